@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: takes more than ~30 s")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the in-tree libraries exist (build() is a no-op when they are up to date)."""
+    import __graft_entry__ as entry
+    entry.build(quiet=True)

@@ -1,0 +1,279 @@
+// xs_device.cuh -- device-side building blocks of the sm_100a XS-lookup engine.
+//
+// Everything here is written for Blackwell (compile: -gencode arch=compute_100a,code=sm_100a
+// -fmad=false).  -fmad=false matters: the reference CPU build targets baseline x86-64 (no
+// FMA), so with contraction off every product/difference below rounds exactly like the
+// reference and the only numerical difference left is the order in which the per-nuclide
+// contributions are summed (warp reductions).
+//
+// Reference behaviour restated (citations relative to ANL-CESAR/XSBench v20):
+//   lcg_*            cuda/Simulation.cu:326-362
+//   pick_material    cuda/Simulation.cu:287-324
+//   ueg_row          cuda/Simulation.cu:241-261   (grid_search; closed form in SURVEY A.2)
+//   nuclide_low_*    cuda/Simulation.cu:102-165   (index selection part of calculate_micro_xs)
+//   interpolate      cuda/Simulation.cu:168-183
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XS_DEV __device__ __forceinline__
+
+namespace xs {
+
+constexpr int kUnionized = 0, kNuclide = 1, kHash = 2;
+constexpr int kNumMaterials = 12;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------
+// Device view of the problem.  Passed to kernels by value (like the reference passes
+// SimulationData), lives in the kernel parameter constant bank.
+// ---------------------------------------------------------------------------------------
+struct Problem {
+    const double  *ueg;          // [n_ueg]            unionized energy grid (unionized only)
+    const int     *index_grid;   // [n_ueg*n_iso] or [hash_bins*n_iso]
+    const double2 *grid;         // nuclide grid viewed as 16-byte chunks: point = 3 chunks
+                                 //   chunk0 = (energy,total) chunk1 = (elastic,absorbtion)
+                                 //   chunk2 = (fission,nu_fission)
+    const uint32_t *ueg_bucket;  // [n_buckets+1]      bucket -> first UEG row in it
+    const int     *mat_first;    // [13]  CSR offsets of the compact material table
+    const int     *mat_nuc;      // [mat_first[12]]    nuclide id
+    const double  *mat_conc;     // [mat_first[12]]    concentration
+    long   n_ueg;
+    double bucket_scale;         // (double)n_buckets
+    int    n_buckets;
+    int    n_iso;
+    int    n_gp;
+    int    hash_bins;
+    int    mat_total;            // mat_first[12]
+};
+
+__constant__ double c_mat_threshold[kNumMaterials];
+
+// ---------------------------------------------------------------------------------------
+// LCG: x <- (a x + 1) mod 2^63
+// ---------------------------------------------------------------------------------------
+constexpr uint64_t kLcgA = 2806196910506780709ULL;
+constexpr uint64_t kLcgMask = 0x7fffffffffffffffULL;
+constexpr uint64_t kStartSeed = 1070ULL;
+
+struct Affine { uint64_t m, c; };           // x -> m x + c   (mod 2^64, masked on use)
+
+XS_DEV uint64_t lcg_step(uint64_t s) { return (kLcgA * s + 1ULL) & kLcgMask; }
+XS_DEV double   lcg_to_double(uint64_t s) { return __ull2double_rn(s) * 0x1p-63; }
+XS_DEV uint64_t apply(Affine f, uint64_t s) { return (f.m * s + f.c) & kLcgMask; }
+
+// The n-step jump as an affine map (same binary decomposition as fast_forward_LCG).
+XS_DEV Affine lcg_jump(uint64_t n)
+{
+    uint64_t sm = kLcgA, sc = 1ULL;
+    Affine r{1ULL, 0ULL};
+    for (n &= kLcgMask; n; n >>= 1) {
+        if (n & 1ULL) { r.m *= sm; r.c = r.c * sm + sc; }
+        sc *= sm + 1ULL;
+        sm *= sm;
+    }
+    return r;
+}
+XS_DEV uint64_t lcg_skip(uint64_t s, uint64_t n) { return apply(lcg_jump(n), s); }
+
+// First i with roll < thr[i] (thr[0] == 0 never matches), else 0 = fuel.
+XS_DEV int pick_material(double roll)
+{
+    int m = 0;
+#pragma unroll
+    for (int i = kNumMaterials - 1; i >= 1; i--)
+        if (roll < c_mat_threshold[i]) m = i;     // descending scan keeps the FIRST match
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------
+// Loads.  Read-only (.nc) path; eviction-priority hints keep the small, hot search
+// structures in L2 while the 5.7 GB index grid streams through.
+// ---------------------------------------------------------------------------------------
+XS_DEV double2 ldg_grid(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+XS_DEV double ldg_grid_energy(const double2 *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// L2 eviction-priority policies (createpolicy): evict_last for the small hot search
+// structures, evict_first for the streamed index-grid rows.  On sm_100a the bare
+// ".L2::evict_*" qualifier exists only for 256-bit loads; narrower loads take a policy
+// operand through ".L2::cache_hint".
+XS_DEV uint64_t policy_keep()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+XS_DEV uint64_t policy_stream()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+XS_DEV int ldg_index_stream(const int *p)         // index grid row: touched once, stream it
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
+                 : "=r"(v) : "l"(p), "l"(policy_stream()));
+    return v;
+}
+XS_DEV int ldg_index_keep(const int *p)           // hash grid: 13.5 MiB, keep it in L2
+{
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy_keep()));
+    return v;
+}
+XS_DEV double ldg_keep_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy_keep()));
+    return v;
+}
+XS_DEV uint32_t ldg_keep_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy_keep()));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Unionized grid: row = grid_search(n_ueg, E, ueg) = clamp(upper_bound(E) - 1, 0, n-2).
+// A bucket table over the value range replaces the top of the binary search: bucket b holds
+// the rows whose energy maps to b under the SAME monotone function used for the query, so
+// upper_bound(E) lies in [bucket[b], bucket[b+1]] and only that span is searched.
+// Usable per lane (each lane may search its own energy).
+// ---------------------------------------------------------------------------------------
+XS_DEV int bucket_of(double e, double scale, int n_buckets)
+{
+    int b = (int)(e * scale);
+    return b < 0 ? 0 : (b >= n_buckets ? n_buckets - 1 : b);
+}
+
+XS_DEV long ueg_row(const Problem &P, double e)
+{
+    const int b = bucket_of(e, P.bucket_scale, P.n_buckets);
+    long lo = ldg_keep_u32(P.ueg_bucket + b);          // rows [lo, hi) are in bucket b
+    long hi = ldg_keep_u32(P.ueg_bucket + b + 1);
+    // upper_bound within [lo, hi): first row with ueg > e
+    while (hi - lo > 4) {
+        const long mid = lo + (hi - lo) / 2;
+        if (ldg_keep_f64(P.ueg + mid) > e) hi = mid; else lo = mid + 1;
+    }
+    while (lo < hi && !(ldg_keep_f64(P.ueg + lo) > e)) lo++;
+    long row = lo - 1;
+    if (row < 0) row = 0;
+    if (row > P.n_ueg - 2) row = P.n_ueg - 2;
+    return row;
+}
+
+// grid_search_nuclide on the energy field of one nuclide's points (48-byte stride).
+XS_DEV int search_nuclide(const double2 *g, double e, int lo, int hi)
+{
+    while (hi - lo > 1) {
+        const int mid = lo + (hi - lo) / 2;
+        if (ldg_grid_energy(g + 3 * (long)mid) > e) hi = mid; else lo = mid;
+    }
+    return lo;
+}
+
+// Index of the lower bounding grid point of nuclide `nuc` for energy e.
+//   unionized: index_grid[row][nuc]; nuclide: full search; hash: bracketed search.
+// `where` is the UEG row (unionized) or the hash bin (hash); unused for nuclide.
+template <int GRID>
+XS_DEV int nuclide_low(const Problem &P, double e, long where, int nuc)
+{
+    const int last = P.n_gp - 1;
+    int low;
+    if (GRID == kUnionized) {
+        low = ldg_index_stream(P.index_grid + where * P.n_iso + nuc);
+    } else if (GRID == kNuclide) {
+        low = search_nuclide(P.grid + 3 * (long)nuc * P.n_gp, e, 0, last);
+    } else {
+        const double2 *g = P.grid + 3 * (long)nuc * P.n_gp;
+        const int u_lo = ldg_index_keep(P.index_grid + where * P.n_iso + nuc);
+        const int u_hi = (where == P.hash_bins - 1)
+                             ? last
+                             : ldg_index_keep(P.index_grid + (where + 1) * P.n_iso + nuc) + 1;
+        const double e_lo = ldg_grid_energy(g + 3 * (long)u_lo);
+        const double e_hi = ldg_grid_energy(g + 3 * (long)u_hi);
+        if (e <= e_lo)      low = 0;
+        else if (e >= e_hi) low = last;
+        else                low = search_nuclide(g, e, u_lo, u_hi);
+    }
+    return low == last ? last - 1 : low;
+}
+
+// Hash bin of an energy: two roundings, exactly like the reference (du = 1/bins; E/du).
+XS_DEV long hash_bin(const Problem &P, double e)
+{
+    const double du = 1.0 / (double)P.hash_bins;
+    long b = (long)(e / du);
+    return b > P.hash_bins - 1 ? P.hash_bins - 1 : b;   // E == 1.0 would read out of bounds
+}
+
+template <int GRID>
+XS_DEV long locate(const Problem &P, double e)
+{
+    if (GRID == kUnionized) return ueg_row(P, e);
+    if (GRID == kHash)      return hash_bin(P, e);
+    return -1;
+}
+
+// hi - f*(hi - lo), f = (hi.E - E)/(hi.E - lo.E)
+XS_DEV double lerp_xs(double lo, double hi, double f) { return hi - f * (hi - lo); }
+
+// ---------------------------------------------------------------------------------------
+// Serial, reference-order evaluation of one macroscopic lookup by a single thread.  Used
+// (rarely) to settle near-ties so that integer results never depend on reduction order,
+// and by the one-thread-per-lookup parity kernel.
+// ---------------------------------------------------------------------------------------
+template <int GRID>
+__device__ __noinline__ void macro_xs_serial(const Problem &P, double e, int mat, double out[5])
+{
+    const long where = locate<GRID>(P, e);
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int first = P.mat_first[mat], n = P.mat_first[mat + 1] - first;
+    for (int j = 0; j < n; j++) {
+        const int nuc = P.mat_nuc[first + j];
+        const double conc = P.mat_conc[first + j];
+        const int low = nuclide_low<GRID>(P, e, where, nuc);
+        const double2 *p = P.grid + 3 * ((long)nuc * P.n_gp + low);
+        const double2 l0 = ldg_grid(p), l1 = ldg_grid(p + 1), l2 = ldg_grid(p + 2);
+        const double2 h0 = ldg_grid(p + 3), h1 = ldg_grid(p + 4), h2 = ldg_grid(p + 5);
+        const double f = (h0.x - e) / (h0.x - l0.x);
+        acc[0] += lerp_xs(l0.y, h0.y, f) * conc;
+        acc[1] += lerp_xs(l1.x, h1.x, f) * conc;
+        acc[2] += lerp_xs(l1.y, h1.y, f) * conc;
+        acc[3] += lerp_xs(l2.x, h2.x, f) * conc;
+        acc[4] += lerp_xs(l2.y, h2.y, f) * conc;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) out[k] = acc[k];
+}
+
+// First index of the strict maximum with start value -1.0 (cuda/Simulation.cu:88-97), plus
+// the relative gap between the two largest values (for the near-tie guard).
+XS_DEV int argmax5(const double v[5], double &rel_gap)
+{
+    double best = -1.0, second = -1.0;
+    int at = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (v[k] > best) { second = best; best = v[k]; at = k; }
+        else if (v[k] > second) second = v[k];
+    }
+    rel_gap = (best - second) / best;
+    return at;
+}
+
+}  // namespace xs

@@ -1,0 +1,745 @@
+// xs_gpu.cu -- C-ABI implementation (include/xs_gpu.h): context, upload, dispatch, timing.
+//
+// Replaces, behind xs_gpu_init / xs_gpu_run / xs_gpu_finalize, the reference's
+// move_simulation_data_to_device (cuda/GridInit.cu:4-78), the seven
+// run_event_based_simulation_* drivers (cuda/Simulation.cu:15,388,521,637,754,895,1024),
+// run_history_based_simulation (openmp-threading/Simulation.c:116-238) and
+// release_device_memory (cuda/GridInit.cu:81-88).
+//
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "xs_gpu.h"
+#include "xs_kernels.cuh"
+#include "xs_sort.cuh"
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return set_error(XS_ERR_CUDA, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call,   \
+                             cudaGetErrorString(err__));                                       \
+    } while (0)
+
+double wall_seconds()
+{
+    using clk = std::chrono::steady_clock;
+    return std::chrono::duration<double>(clk::now().time_since_epoch()).count();
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+enum { EV_START = 0, EV_SAMPLED, EV_SORTED, EV_LOOKED_UP, EV_DONE, EV_COUNT };
+
+struct DeviceState {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    long l2_bytes = 0;
+    // problem
+    unsigned char *hot_slab = nullptr;     // [bucket table | UEG] or hash index: L2-persisting
+    size_t hot_bytes = 0;
+    int *index_grid = nullptr;             // unionized index grid (streamed)
+    double2 *grid = nullptr;
+    int *mat_first = nullptr, *mat_nuc = nullptr;
+    double *mat_conc = nullptr;
+    xs::Problem P{};
+    size_t resident_bytes = 0;
+    // per-run scratch
+    unsigned long long *accum = nullptr;   // device [2]
+    unsigned int *counters = nullptr;      // device [16]: batch counters
+    unsigned int *histogram = nullptr;     // device [16]
+    unsigned long long *h_accum = nullptr; // pinned host [2]
+    unsigned int *h_hist = nullptr;        // pinned host [16]
+    long sample_capacity = 0;
+    double *samp_e = nullptr;
+    int *samp_mat = nullptr;
+    uint32_t *key[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
+    xs::SortScratch sort{};
+    double *dump_macro = nullptr;          // staging for macro_xs output
+    long dump_capacity = 0;
+    cudaEvent_t ev[EV_COUNT] = {};
+    int launches = 0;
+};
+
+}  // namespace
+
+struct xs_gpu_ctx {
+    std::vector<DeviceState> dev;
+    int grid_type = 0;
+    long n_iso = 0, n_gp = 0;
+    int hash_bins = 0, max_num_nucs = 0;
+    long n_ueg = 0;
+    int gather = xs::kTriple;
+    int blocks_per_sm = 0;                 // 0 = from occupancy
+    size_t smem_bytes = 0;
+    void *nccl = nullptr;                  // multi-GPU collective state (xs_multi.cuh)
+};
+
+#include "xs_multi.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// kernel selection
+// ---------------------------------------------------------------------------------------
+typedef void (*EventKernel)(const xs::Problem, const xs::BatchSource, const xs::BatchSink);
+typedef void (*HistoryKernel)(const xs::Problem, long, long, int, const xs::BatchSink);
+
+EventKernel event_kernel(int grid, int gather)
+{
+    using namespace xs;
+    static const EventKernel table[3][2] = {
+        { xs_event_kernel<kUnionized, kLanePerNuclide>, xs_event_kernel<kUnionized, kTriple> },
+        { xs_event_kernel<kNuclide,   kLanePerNuclide>, xs_event_kernel<kNuclide,   kTriple> },
+        { xs_event_kernel<kHash,      kLanePerNuclide>, xs_event_kernel<kHash,      kTriple> },
+    };
+    return table[grid][gather];
+}
+
+HistoryKernel history_kernel(int grid, int gather)
+{
+    using namespace xs;
+    static const HistoryKernel table[3][2] = {
+        { xs_history_kernel<kUnionized, kLanePerNuclide>, xs_history_kernel<kUnionized, kTriple> },
+        { xs_history_kernel<kNuclide,   kLanePerNuclide>, xs_history_kernel<kNuclide,   kTriple> },
+        { xs_history_kernel<kHash,      kLanePerNuclide>, xs_history_kernel<kHash,      kTriple> },
+    };
+    return table[grid][gather];
+}
+
+int persistent_grid(const xs_gpu_ctx *ctx, const DeviceState &d, const void *kernel, int *blocks)
+{
+    int per_sm = ctx->blocks_per_sm;
+    if (per_sm <= 0) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, xs::kBlockThreads,
+                                                               ctx->smem_bytes));
+        if (per_sm < 1) per_sm = 1;
+    }
+    *blocks = per_sm * d.sm_count;
+    return XS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------
+int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const SimulationData *sd,
+                  const DeviceState *peer)
+{
+    CUDA_TRY(cudaSetDevice(d.device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, d.device));
+    d.sm_count = prop.multiProcessorCount;
+    d.l2_bytes = prop.l2CacheSize;
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    d.own_stream = true;
+    for (int i = 0; i < EV_COUNT; i++) CUDA_TRY(cudaEventCreate(&d.ev[i]));
+
+    const long n_iso = in->n_isotopes, n_gp = in->n_gridpoints;
+    const long n_points = n_iso * n_gp;
+    xs::Problem &P = d.P;
+    P.n_iso = (int)n_iso;
+    P.n_gp = (int)n_gp;
+    P.hash_bins = in->hash_bins;
+
+    auto copy_in = [&](void *dst, const void *host_src, const void *peer_src, size_t bytes) -> cudaError_t {
+        if (peer) return cudaMemcpyPeerAsync(dst, d.device, peer_src, peer->device, bytes, d.stream);
+        return cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, d.stream);
+    };
+
+    // nuclide grid (48-byte points, viewed as 16-byte chunks)
+    const size_t grid_bytes = (size_t)n_points * sizeof(NuclideGridPoint);
+    CUDA_TRY(cudaMalloc(&d.grid, grid_bytes));
+    CUDA_TRY(copy_in(d.grid, sd->nuclide_grid, peer ? peer->grid : nullptr, grid_bytes));
+    d.resident_bytes += grid_bytes;
+    P.grid = d.grid;
+
+    // search structures
+    if (ctx->grid_type == XS_UNIONIZED) {
+        const long n_ueg = sd->length_unionized_energy_array;
+        long n_buckets = n_ueg / 2;
+        if (n_buckets < 1) n_buckets = 1;
+        if (n_buckets > (1L << 24)) n_buckets = 1L << 24;
+        n_buckets = env_int("XSB200_BUCKETS", (int)n_buckets);
+        const size_t bucket_bytes = (((size_t)n_buckets + 1) * sizeof(uint32_t) + 255) / 256 * 256;
+        const size_t ueg_bytes = (size_t)n_ueg * sizeof(double);
+        d.hot_bytes = bucket_bytes + ueg_bytes;
+        CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
+        uint32_t *bucket = reinterpret_cast<uint32_t *>(d.hot_slab);
+        double *ueg = reinterpret_cast<double *>(d.hot_slab + bucket_bytes);
+        CUDA_TRY(copy_in(ueg, sd->unionized_energy_array,
+                         peer ? peer->hot_slab + bucket_bytes : nullptr, ueg_bytes));
+        xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(
+            ueg, n_ueg, (double)n_buckets, (int)n_buckets, bucket);
+        CUDA_TRY(cudaGetLastError());
+        const size_t index_bytes = (size_t)sd->length_index_grid * sizeof(int);
+        CUDA_TRY(cudaMalloc(&d.index_grid, index_bytes));
+        CUDA_TRY(copy_in(d.index_grid, sd->index_grid, peer ? peer->index_grid : nullptr, index_bytes));
+        d.resident_bytes += d.hot_bytes + index_bytes;
+        P.ueg = ueg;
+        P.ueg_bucket = bucket;
+        P.n_ueg = n_ueg;
+        P.n_buckets = (int)n_buckets;
+        P.bucket_scale = (double)n_buckets;
+        P.index_grid = d.index_grid;
+    } else if (ctx->grid_type == XS_HASH) {
+        d.hot_bytes = (size_t)sd->length_index_grid * sizeof(int);
+        CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
+        CUDA_TRY(copy_in(d.hot_slab, sd->index_grid, peer ? peer->hot_slab : nullptr, d.hot_bytes));
+        d.resident_bytes += d.hot_bytes;
+        P.index_grid = reinterpret_cast<const int *>(d.hot_slab);
+    }
+
+    // compact (CSR) material tables
+    int first[XS_NUM_MATERIALS + 1];
+    first[0] = 0;
+    for (int m = 0; m < XS_NUM_MATERIALS; m++) first[m + 1] = first[m] + sd->num_nucs[m];
+    const int total = first[XS_NUM_MATERIALS];
+    std::vector<int> nuc(total);
+    std::vector<double> conc(total);
+    for (int m = 0; m < XS_NUM_MATERIALS; m++)
+        for (int j = 0; j < sd->num_nucs[m]; j++) {
+            nuc[first[m] + j] = sd->mats[(size_t)m * sd->max_num_nucs + j];
+            conc[first[m] + j] = sd->concs[(size_t)m * sd->max_num_nucs + j];
+        }
+    CUDA_TRY(cudaMalloc(&d.mat_first, sizeof first));
+    CUDA_TRY(cudaMalloc(&d.mat_nuc, (size_t)total * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d.mat_conc, (size_t)total * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(d.mat_first, first, sizeof first, cudaMemcpyHostToDevice, d.stream));
+    CUDA_TRY(cudaMemcpyAsync(d.mat_nuc, nuc.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+    CUDA_TRY(cudaMemcpyAsync(d.mat_conc, conc.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    P.mat_first = d.mat_first;
+    P.mat_nuc = d.mat_nuc;
+    P.mat_conc = d.mat_conc;
+    P.mat_total = total;
+    ctx->smem_bytes = sizeof(xs::SharedTables) + (size_t)total * (sizeof(double) + sizeof(int));
+
+    // material thresholds: same summation order as pick_mat (cuda/Simulation.cu:314-321)
+    static const double frac[XS_NUM_MATERIALS] = { 0.140, 0.052, 0.275, 0.134, 0.154, 0.064,
+                                                   0.066, 0.055, 0.008, 0.015, 0.025, 0.013 };
+    double thr[XS_NUM_MATERIALS];
+    for (int i = 0; i < XS_NUM_MATERIALS; i++) {
+        double acc = 0.0;
+        for (int j = i; j >= 1; j--) acc += frac[j];
+        thr[i] = acc;
+    }
+    CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_mat_threshold, thr, sizeof thr, 0, cudaMemcpyHostToDevice, d.stream));
+
+    // run scratch
+    CUDA_TRY(cudaMalloc(&d.accum, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d.counters, 16 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&d.histogram, 16 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMallocHost(&d.h_accum, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&d.h_hist, 16 * sizeof(unsigned int)));
+
+    CUDA_TRY(cudaStreamSynchronize(d.stream));   // host vectors above go out of scope
+
+    // L2 residency for the hot search structures (bucket table + UEG, or the hash grid):
+    // a persisting access-policy window on this stream.  The per-load evict_last /
+    // evict_first hints in xs_device.cuh work with or without it.
+    if (d.hot_slab && env_int("XSB200_L2_WINDOW", 1)) {
+        size_t want = std::min<size_t>(d.hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = d.hot_slab;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(d.hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            cudaStreamSetAttribute(d.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        }
+        cudaGetLastError();   // residency is an optimisation; never fatal
+    }
+    return XS_OK;
+}
+
+int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
+{
+    CUDA_TRY(cudaSetDevice(d.device));
+    if (n > d.sample_capacity) {
+        cudaFree(d.samp_e); cudaFree(d.samp_mat);
+        for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); d.key[i] = d.perm[i] = nullptr; }
+        d.samp_e = nullptr; d.samp_mat = nullptr;
+        CUDA_TRY(cudaMalloc(&d.samp_e, (size_t)n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.samp_mat, (size_t)n * sizeof(int)));
+        d.sample_capacity = n;
+    }
+    if (need_sort && !d.key[0]) {
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaMalloc(&d.key[i], (size_t)d.sample_capacity * sizeof(uint32_t)));
+            CUDA_TRY(cudaMalloc(&d.perm[i], (size_t)d.sample_capacity * sizeof(uint32_t)));
+        }
+        int rc = xs::sort_scratch_alloc(d.sort, d.sample_capacity);
+        if (rc != 0) return set_error(XS_ERR_CUDA, "sort scratch allocation failed");
+    }
+    return XS_OK;
+}
+
+int ensure_dump_buffer(DeviceState &d, long n)
+{
+    if (n > d.dump_capacity) {
+        cudaFree(d.dump_macro);
+        d.dump_macro = nullptr;
+        CUDA_TRY(cudaMalloc(&d.dump_macro, (size_t)n * 5 * sizeof(double)));
+        d.dump_capacity = n;
+    }
+    return XS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------
+int launch_event(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs::BatchSink sink,
+                 int counter_slot)
+{
+    if (src.count <= 0) return XS_OK;
+    EventKernel k = event_kernel(ctx->grid_type, ctx->gather);
+    int blocks = 0;
+    int rc = persistent_grid(ctx, d, (const void *)k, &blocks);
+    if (rc != XS_OK) return rc;
+    const long n_batches = (src.count + 31) / 32;
+    const long max_useful = (n_batches + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+    if (blocks > max_useful) blocks = (int)max_useful;
+    sink.batch_counter = d.counters + counter_slot;
+    k<<<blocks, xs::kBlockThreads, ctx->smem_bytes, d.stream>>>(d.P, src, sink);
+    CUDA_TRY(cudaGetLastError());
+    d.launches++;
+    return XS_OK;
+}
+
+int launch_sample(DeviceState &d, long first_id, long count, bool with_key, bool with_hist)
+{
+    int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
+    xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(first_id, count, d.samp_e, d.samp_mat,
+                                                       with_key ? d.key[0] : nullptr,
+                                                       with_hist ? d.histogram : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    d.launches++;
+    return XS_OK;
+}
+
+// One device's share of an event-mode run: ids [first_id, first_id + count).
+int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count)
+{
+    CUDA_TRY(cudaSetDevice(d.device));
+    d.launches = 0;
+    CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.histogram, 0, 16 * sizeof(unsigned int), d.stream));
+
+    xs::BatchSink sink{};
+    sink.accum = d.accum;
+    xs::BatchSource src{};
+    src.first_id = first_id;
+    src.count = count;
+    src.mat_lo = 0;
+    src.mat_hi = XS_NUM_MATERIALS - 1;
+    int rc = XS_OK;
+
+    if (kernel_id == 0) {
+        // baseline semantics (cuda/Simulation.cu:44-99): sample + lookup fused, one launch
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+        rc = launch_event(ctx, d, src, sink, 0);
+    } else {
+        const bool sorted = kernel_id == 4 || kernel_id == 5 || kernel_id == 6;
+        if ((rc = ensure_sample_buffers(d, count, sorted)) != XS_OK) return rc;
+        if ((rc = launch_sample(d, first_id, count, sorted, sorted)) != XS_OK) return rc;
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+        src.energy = d.samp_e;
+        src.mat = d.samp_mat;
+        if (!sorted) {
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+            if (kernel_id == 1) {
+                // optimization 1 (cuda/Simulation.cu:388-439): split sample / lookup
+                rc = launch_event(ctx, d, src, sink, 0);
+            } else if (kernel_id == 2) {
+                // optimization 2 (:521-574): one launch per material, unsorted samples
+                for (int m = 0; m < XS_NUM_MATERIALS && rc == XS_OK; m++) {
+                    src.mat_lo = src.mat_hi = m;
+                    rc = launch_event(ctx, d, src, sink, m);
+                }
+            } else {
+                // optimization 3 (:637-690): fuel launch + everything-else launch
+                src.mat_lo = src.mat_hi = 0;
+                rc = launch_event(ctx, d, src, sink, 0);
+                src.mat_lo = 1; src.mat_hi = XS_NUM_MATERIALS - 1;
+                if (rc == XS_OK) rc = launch_event(ctx, d, src, sink, 1);
+            }
+        } else {
+            // optimizations 4/5/6 (:754-821, :895-958, :1024-1099): reorder the lookups with
+            // the hand-written radix sort, then launch per contiguous material range.
+            //   4: key = material            (4 bits)
+            //   5: key = fuel / not fuel     (1 bit; the partition the reference intended)
+            //   6: key = material | energy   (32 bits)
+            int key_lo_bit = 28, key_hi_bit = 32;
+            if (kernel_id == 6) key_lo_bit = 0;
+            uint32_t *sorted_perm = nullptr;
+            int src_is_fuel_bit = (kernel_id == 5);
+            rc = xs::sort_lookups(d.sort, d.key, d.perm, count, key_lo_bit, key_hi_bit,
+                                  src_is_fuel_bit, d.stream, &sorted_perm, &d.launches);
+            if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+            // per-material counts were produced by the sampling kernel
+            CUDA_TRY(cudaMemcpyAsync(d.h_hist, d.histogram, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            long offset = 0;
+            const int n_groups = (kernel_id == 5) ? 2 : XS_NUM_MATERIALS;
+            for (int g = 0; g < n_groups && rc == XS_OK; g++) {
+                long n_g = 0;
+                if (kernel_id == 5) {
+                    if (g == 0) n_g = d.h_hist[0];
+                    else for (int m = 1; m < XS_NUM_MATERIALS; m++) n_g += d.h_hist[m];
+                } else n_g = d.h_hist[g];
+                xs::BatchSource part = src;
+                part.perm = sorted_perm + offset;
+                part.count = n_g;
+                rc = launch_event(ctx, d, part, sink, g);
+                offset += n_g;
+            }
+        }
+    }
+    if (rc != XS_OK) return rc;
+    CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
+    return XS_OK;
+}
+
+int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n_particles, int lookups)
+{
+    CUDA_TRY(cudaSetDevice(d.device));
+    d.launches = 0;
+    CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+    CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+    if (n_particles > 0) {
+        HistoryKernel k = history_kernel(ctx->grid_type, ctx->gather);
+        int blocks = 0;
+        int rc = persistent_grid(ctx, d, (const void *)k, &blocks);
+        if (rc != XS_OK) return rc;
+        const long max_useful = (n_particles + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+        if (blocks > max_useful) blocks = (int)max_useful;
+        xs::BatchSink sink{};
+        sink.accum = d.accum;
+        sink.batch_counter = d.counters;
+        k<<<blocks, xs::kBlockThreads, ctx->smem_bytes, d.stream>>>(d.P, first_particle, n_particles, lookups, sink);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
+    }
+    CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
+    return XS_OK;
+}
+
+// Collect {verification, n_lookups}: all-reduce across devices (NCCL) when n_gpus > 1, then
+// device -> pinned host, and fill the timing fields.
+int finish_run(xs_gpu_ctx *ctx, xs_gpu_result *res, double host_t0)
+{
+    const int n = (int)ctx->dev.size();
+    if (n > 1) {
+        int rc = xs_multi_allreduce(ctx);
+        if (rc != XS_OK) return rc;
+    }
+    for (int g = 0; g < n; g++) {
+        DeviceState &d = ctx->dev[g];
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(cudaMemcpyAsync(d.h_accum, d.accum, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_DONE], d.stream));
+    }
+    memset(res, 0, sizeof *res);
+    for (int g = 0; g < n; g++) {
+        DeviceState &d = ctx->dev[g];
+        CUDA_TRY(cudaSetDevice(d.device));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        float ms[4], total = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&total, d.ev[EV_START], d.ev[EV_DONE]));
+        for (int p = 0; p < 4; p++) CUDA_TRY(cudaEventElapsedTime(&ms[p], d.ev[p], d.ev[p + 1]));
+        res->device_seconds = std::max(res->device_seconds, (double)total * 1e-3);
+        for (int p = 0; p < 4; p++) res->phase_seconds[p] = std::max(res->phase_seconds[p], (double)ms[p] * 1e-3);
+        res->gpu_launches += d.launches;
+        res->d2h_bytes += 2 * sizeof(unsigned long long);
+    }
+    CUDA_TRY(cudaSetDevice(ctx->dev[0].device));
+    res->verification = ctx->dev[0].h_accum[0];     // all-reduced: identical on every device
+    res->n_lookups = ctx->dev[0].h_accum[1];
+    res->host_seconds = wall_seconds() - host_t0;
+    res->n_gpus = n;
+    return XS_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char *xs_gpu_last_error(void) { return g_error; }
+const char *xs_gpu_version(void) { return "xsbench_b200 0.1 (sm_100a)"; }
+
+int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_ctx **out)
+{
+    if (!in || !sd || !out) return set_error(XS_ERR_ARG, "xs_gpu_init: NULL argument");
+    *out = nullptr;
+    if (n_gpus < 1 || n_gpus > 8) return set_error(XS_ERR_ARG, "xs_gpu_init: n_gpus must be 1..8");
+    if (in->grid_type < 0 || in->grid_type > 2) return set_error(XS_ERR_ARG, "xs_gpu_init: bad grid_type %d", in->grid_type);
+    if (in->n_isotopes < 1 || in->n_gridpoints < 2) return set_error(XS_ERR_ARG, "xs_gpu_init: bad problem size");
+    if (!sd->nuclide_grid || !sd->num_nucs || !sd->mats || !sd->concs)
+        return set_error(XS_ERR_ARG, "xs_gpu_init: SimulationData has NULL arrays");
+    if (sd->length_nuclide_grid != in->n_isotopes * in->n_gridpoints)
+        return set_error(XS_ERR_ARG, "xs_gpu_init: length_nuclide_grid does not match Inputs");
+    if (in->grid_type == XS_UNIONIZED &&
+        (!sd->unionized_energy_array || !sd->index_grid ||
+         sd->length_index_grid != (long)sd->length_unionized_energy_array * in->n_isotopes))
+        return set_error(XS_ERR_ARG, "xs_gpu_init: unionized grid arrays missing or inconsistent");
+    if (in->grid_type == XS_HASH &&
+        (!sd->index_grid || in->hash_bins < 1 || sd->length_index_grid != (long)in->hash_bins * in->n_isotopes))
+        return set_error(XS_ERR_ARG, "xs_gpu_init: hash grid missing or inconsistent");
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev < 1)
+        return set_error(XS_ERR_CUDA, "xs_gpu_init: no CUDA device (%s); this library has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int dev0 = 0;
+    CUDA_TRY(cudaGetDevice(&dev0));
+    if (dev0 + n_gpus > n_dev)
+        return set_error(XS_ERR_ARG, "xs_gpu_init: %d GPUs requested from device %d but only %d present", n_gpus, dev0, n_dev);
+
+    xs_gpu_ctx *ctx = new (std::nothrow) xs_gpu_ctx;
+    if (!ctx) return set_error(XS_ERR_ARG, "out of host memory");
+    ctx->grid_type = in->grid_type;
+    ctx->n_iso = in->n_isotopes;
+    ctx->n_gp = in->n_gridpoints;
+    ctx->hash_bins = in->hash_bins;
+    ctx->max_num_nucs = sd->max_num_nucs;
+    ctx->n_ueg = in->grid_type == XS_UNIONIZED ? sd->length_unionized_energy_array : 0;
+    ctx->gather = env_int("XSB200_GATHER", xs::kTriple) ? xs::kTriple : xs::kLanePerNuclide;
+    ctx->blocks_per_sm = env_int("XSB200_BLOCKS_PER_SM", 0);
+    ctx->dev.resize(n_gpus);
+    for (int g = 0; g < n_gpus; g++) ctx->dev[g].device = dev0 + g;
+
+    int rc = XS_OK;
+    for (int g = 0; g < n_gpus && rc == XS_OK; g++) {
+        if (g > 0) {
+            // replicate from GPU 0 over NVLink (peer copy), excluded from the FOM like the
+            // reference's H2D (cuda/Main.cu:42 is before the timer)
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctx->dev[g].device, ctx->dev[0].device);
+            if (can) {
+                cudaSetDevice(ctx->dev[g].device);
+                cudaDeviceEnablePeerAccess(ctx->dev[0].device, 0);
+                cudaGetLastError();
+            }
+        }
+        rc = upload_device(ctx, ctx->dev[g], in, sd, g > 0 ? &ctx->dev[0] : nullptr);
+    }
+    if (rc == XS_OK && in->simulation_method == XS_EVENT_BASED && in->kernel_id != 0 && in->lookups > 0) {
+        // pre-allocate the sample / sort buffers here, not inside the timed region
+        const long per_gpu = ((long)in->lookups + n_gpus - 1) / n_gpus;
+        for (int g = 0; g < n_gpus && rc == XS_OK; g++)
+            rc = ensure_sample_buffers(ctx->dev[g], per_gpu, in->kernel_id >= 4);
+    }
+    if (rc == XS_OK && n_gpus > 1) rc = xs_multi_init(ctx);
+    if (rc != XS_OK) {
+        char keep[sizeof g_error];
+        memcpy(keep, g_error, sizeof keep);
+        xs_gpu_finalize(ctx);
+        memcpy(g_error, keep, sizeof keep);
+        return rc;
+    }
+    cudaSetDevice(dev0);
+    *out = ctx;
+    return XS_OK;
+}
+
+int xs_gpu_run_range(xs_gpu_ctx *ctx, const Inputs *in, long first_id, long count, xs_gpu_result *res)
+{
+    if (!ctx || !in || !res) return set_error(XS_ERR_ARG, "xs_gpu_run: NULL argument");
+    if (count < 0 || first_id < 0) return set_error(XS_ERR_ARG, "xs_gpu_run: negative range");
+    const bool event = in->simulation_method == XS_EVENT_BASED;
+    if (!event && in->simulation_method != XS_HISTORY_BASED)
+        return set_error(XS_ERR_ARG, "xs_gpu_run: unknown simulation_method %d", in->simulation_method);
+    if (event && (in->kernel_id < 0 || in->kernel_id > 6))
+        return set_error(XS_ERR_ARG, "xs_gpu_run: no kernel ID %d", in->kernel_id);
+    if (!event && in->kernel_id != 0)
+        return set_error(XS_ERR_ARG, "xs_gpu_run: no kernel ID %d for history mode", in->kernel_id);
+    if (!event && in->lookups < 1) return set_error(XS_ERR_ARG, "xs_gpu_run: lookups per particle must be >= 1");
+    if (in->grid_type != ctx->grid_type || in->n_isotopes != ctx->n_iso || in->n_gridpoints != ctx->n_gp)
+        return set_error(XS_ERR_ARG, "xs_gpu_run: Inputs do not match the problem uploaded by xs_gpu_init");
+
+    const double t0 = wall_seconds();
+    const int n = (int)ctx->dev.size();
+    for (int g = 0; g < n; g++) {
+        const long lo = first_id + count * g / n, hi = first_id + count * (g + 1) / n;
+        int rc = event ? enqueue_event(ctx, ctx->dev[g], in->kernel_id, lo, hi - lo)
+                       : enqueue_history(ctx, ctx->dev[g], lo, hi - lo, in->lookups);
+        if (rc != XS_OK) return rc;
+    }
+    return finish_run(ctx, res, t0);
+}
+
+int xs_gpu_run(xs_gpu_ctx *ctx, const Inputs *in, xs_gpu_result *res)
+{
+    if (!in) return set_error(XS_ERR_ARG, "xs_gpu_run: NULL argument");
+    const long count = in->simulation_method == XS_EVENT_BASED ? (long)in->lookups : (long)in->particles;
+    return xs_gpu_run_range(ctx, in, 0, count, res);
+}
+
+int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_mat, long n,
+                          double *h_macro_xs_out, xs_gpu_result *res)
+{
+    if (!ctx || !h_energy || !h_mat || !res || n < 0)
+        return set_error(XS_ERR_ARG, "xs_gpu_lookup_samples: bad argument");
+    const double t0 = wall_seconds();
+    const int ng = (int)ctx->dev.size();
+    for (int g = 0; g < ng; g++) {
+        DeviceState &d = ctx->dev[g];
+        const long lo = n * g / ng, cnt = n * (g + 1) / ng - lo;
+        int rc = ensure_sample_buffers(d, cnt, false);
+        if (rc == XS_OK && h_macro_xs_out) rc = ensure_dump_buffer(d, cnt);
+        if (rc != XS_OK) return rc;
+        CUDA_TRY(cudaSetDevice(d.device));
+        d.launches = 0;
+        CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+        CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaMemcpyAsync(d.samp_mat, h_mat + lo, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+        xs::BatchSource src{};
+        src.energy = d.samp_e; src.mat = d.samp_mat; src.count = cnt;
+        src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
+        xs::BatchSink sink{};
+        sink.accum = d.accum;
+        sink.macro_out = h_macro_xs_out ? d.dump_macro : nullptr;
+        rc = launch_event(ctx, d, src, sink, 0);
+        if (rc != XS_OK) return rc;
+        if (h_macro_xs_out)
+            CUDA_TRY(cudaMemcpyAsync(h_macro_xs_out + 5 * lo, d.dump_macro, (size_t)cnt * 5 * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
+    }
+    int rc = finish_run(ctx, res, t0);
+    if (rc != XS_OK) return rc;
+    res->h2d_bytes = (unsigned long long)n * (sizeof(double) + sizeof(int));
+    if (h_macro_xs_out) res->d2h_bytes += (unsigned long long)n * 5 * sizeof(double);
+    return XS_OK;
+}
+
+int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, int *h_mat_out,
+                double *h_macro_xs_out, int *h_argmax_out)
+{
+    if (!ctx || n < 0 || first_id < 0) return set_error(XS_ERR_ARG, "xs_gpu_dump: bad argument");
+    if (n == 0) return XS_OK;
+    DeviceState &d = ctx->dev[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    double *d_e = nullptr, *d_macro = nullptr;
+    int *d_mat = nullptr, *d_am = nullptr;
+    CUDA_TRY(cudaMalloc(&d_e, (size_t)n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_macro, (size_t)n * 5 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_mat, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_am, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+    xs::BatchSource src{};
+    src.first_id = first_id; src.count = n; src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
+    xs::BatchSink sink{};
+    sink.accum = d.accum; sink.macro_out = d_macro; sink.energy_out = d_e; sink.mat_out = d_mat; sink.argmax_out = d_am;
+    int rc = launch_event(ctx, d, src, sink, 0);
+    if (rc == XS_OK) {
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        if (e == cudaSuccess && h_energy_out) e = cudaMemcpy(h_energy_out, d_e, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && h_mat_out) e = cudaMemcpy(h_mat_out, d_mat, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && h_macro_xs_out) e = cudaMemcpy(h_macro_xs_out, d_macro, (size_t)n * 5 * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && h_argmax_out) e = cudaMemcpy(h_argmax_out, d_am, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_error(XS_ERR_CUDA, "xs_gpu_dump: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_e); cudaFree(d_macro); cudaFree(d_mat); cudaFree(d_am);
+    return rc;
+}
+
+int xs_gpu_set_stream(xs_gpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return set_error(XS_ERR_ARG, "xs_gpu_set_stream: NULL context");
+    DeviceState &d = ctx->dev[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    if (d.own_stream) cudaStreamDestroy(d.stream);
+    d.stream = (cudaStream_t)cuda_stream;
+    d.own_stream = false;
+    return XS_OK;
+}
+
+int xs_gpu_get_info(const xs_gpu_ctx *ctx, xs_gpu_info *info)
+{
+    if (!ctx || !info) return set_error(XS_ERR_ARG, "xs_gpu_get_info: NULL argument");
+    const DeviceState &d = ctx->dev[0];
+    info->device = d.device;
+    info->sm_count = d.sm_count;
+    info->l2_bytes = d.l2_bytes;
+    info->resident_bytes = (long)d.resident_bytes;
+    info->n_isotopes = ctx->n_iso;
+    info->n_gridpoints = ctx->n_gp;
+    info->grid_type = ctx->grid_type;
+    info->hash_bins = ctx->hash_bins;
+    info->max_num_nucs = ctx->max_num_nucs;
+    info->n_ueg = ctx->n_ueg;
+    return XS_OK;
+}
+
+int xs_gpu_finalize(xs_gpu_ctx *ctx)
+{
+    if (!ctx) return XS_OK;
+    xs_multi_destroy(ctx);
+    for (DeviceState &d : ctx->dev) {
+        if (d.device < 0) continue;
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        cudaFree(d.hot_slab); cudaFree(d.index_grid); cudaFree(d.grid);
+        cudaFree(d.mat_first); cudaFree(d.mat_nuc); cudaFree(d.mat_conc);
+        cudaFree(d.accum); cudaFree(d.counters); cudaFree(d.histogram);
+        cudaFree(d.samp_e); cudaFree(d.samp_mat);
+        for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
+        xs::sort_scratch_free(d.sort);
+        cudaFree(d.dump_macro);
+        if (d.h_accum) cudaFreeHost(d.h_accum);
+        if (d.h_hist) cudaFreeHost(d.h_hist);
+        for (int i = 0; i < EV_COUNT; i++) if (d.ev[i]) cudaEventDestroy(d.ev[i]);
+        if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
+    }
+    cudaGetLastError();
+    delete ctx;
+    return XS_OK;
+}
+
+}  // extern "C"

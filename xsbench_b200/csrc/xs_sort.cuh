@@ -1,0 +1,183 @@
+// xs_sort.cuh -- hand-written LSD radix sort of the sampled lookups (key -> permutation).
+//
+// Replaces the Thrust calls of the reference's sorted variants: 12x thrust::count +
+// thrust::sort_by_key by material (cuda/Simulation.cu:792-797), thrust::partition (:936) and
+// the 12 per-material sort_by_key by energy (:1070-1075).  Here ONE packed 32-bit key
+//     key = material << 28 | top 28 bits of the LCG state behind the energy
+// is sorted, 8 bits per pass, carrying a 32-bit permutation index; the lookup kernel reads
+// its samples through the permutation.  A material-only sort (-k 4) is a single 4-bit pass
+// over bits 28..31, the fuel-first partition (-k 5) a single 1-bit pass.  The passes are
+// stable, so equal keys keep lookup-id order.
+//
+// Each pass = histogram (per 4096-key tile) -> exclusive scan of the digit-major
+// [digit][tile] table -> stable scatter using warp match_any ranking.
+#pragma once
+
+#include "xs_device.cuh"
+
+namespace xs {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                              // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;        // 4096 keys per block
+constexpr int kRadix = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+
+struct SortScratch {
+    unsigned int *tile_hist = nullptr;      // [kRadix][n_tiles]
+    long n_tiles_capacity = 0;
+};
+
+inline int sort_scratch_alloc(SortScratch &s, long capacity_keys)
+{
+    const long tiles = (capacity_keys + kSortTile - 1) / kSortTile;
+    if (tiles <= s.n_tiles_capacity) return 0;
+    cudaFree(s.tile_hist);
+    s.tile_hist = nullptr;
+    if (cudaMalloc(&s.tile_hist, (size_t)tiles * kRadix * sizeof(unsigned int)) != cudaSuccess) return -1;
+    s.n_tiles_capacity = tiles;
+    return 0;
+}
+inline void sort_scratch_free(SortScratch &s) { cudaFree(s.tile_hist); s.tile_hist = nullptr; s.n_tiles_capacity = 0; }
+
+XS_DEV uint32_t sort_digit(uint32_t key, int shift, uint32_t mask, int nonzero_flag)
+{
+    const uint32_t d = (key >> shift) & mask;
+    return nonzero_flag ? (uint32_t)(d != 0) : d;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_hist_kernel(const uint32_t *__restrict__ keys, long n, int shift, uint32_t mask, int nonzero_flag,
+                 unsigned int *__restrict__ tile_hist, int n_tiles)
+{
+    __shared__ unsigned int h[kRadix];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long base = (long)blockIdx.x * kSortTile;
+#pragma unroll 4
+    for (int i = 0; i < kSortItems; i++) {
+        const long idx = base + i * kSortThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[sort_digit(keys[idx], shift, mask, nonzero_flag)], 1u);
+    }
+    __syncthreads();
+    tile_hist[(long)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// In-place exclusive scan of `total` counters by one block of 1024 threads.
+__global__ void __launch_bounds__(1024)
+sort_scan_kernel(unsigned int *data, long total)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long chunk = (total + 1023) / 1024;
+    const long lo = (long)tid * chunk < total ? (long)tid * chunk : total;
+    const long hi = lo + chunk < total ? lo + chunk : total;
+    unsigned int sum = 0;
+    for (long i = lo; i < hi; i++) sum += data[i];
+    // block exclusive scan of the per-thread sums
+    unsigned int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int t = __shfl_up_sync(kFullMask, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int t = __shfl_up_sync(kFullMask, wi, off);
+            if (lane >= off) wi += t;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned int run = warp_sums[warp] + incl - sum;
+    for (long i = lo; i < hi; i++) { const unsigned int v = data[i]; data[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, long n, int shift,
+                    uint32_t mask, int nonzero_flag, const unsigned int *__restrict__ tile_base, int n_tiles)
+{
+    __shared__ unsigned int warp_cnt[kSortWarps][kRadix];
+    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long base = (long)blockIdx.x * kSortTile + (long)warp * (32 * kSortItems);
+    uint32_t key[kSortItems];
+    unsigned short rank[kSortItems];
+
+#pragma unroll
+    for (int r = 0; r < kSortItems; r++) {
+        const long idx = base + r * 32 + lane;
+        const bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0u;
+        const uint32_t d = valid ? sort_digit(key[r], shift, mask, nonzero_flag) : (uint32_t)kRadix;
+        const unsigned peers = __match_any_sync(kFullMask, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned int before = 0;
+        if (valid && lane == leader) {
+            before = warp_cnt[warp][d];
+            warp_cnt[warp][d] = before + __popc(peers);
+        }
+        before = __shfl_sync(kFullMask, before, leader);
+        rank[r] = (unsigned short)(before + __popc(peers & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per digit: warp offsets within the tile + the tile's global base
+        const int d = threadIdx.x;
+        unsigned int run = tile_base[(long)d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            const unsigned int c = warp_cnt[w][d];
+            warp_cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; r++) {
+        const long idx = base + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = sort_digit(key[r], shift, mask, nonzero_flag);
+            const unsigned int pos = warp_cnt[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in ? vals_in[idx] : (uint32_t)idx;
+        }
+    }
+}
+
+// Sort bits [lo_bit, hi_bit) of key[0][0..n).  key[]/perm[] are ping-pong buffers; on return
+// *sorted_perm points at the buffer holding the final permutation.  Returns 0 on success.
+inline int sort_lookups(SortScratch &s, uint32_t *key[2], uint32_t *perm[2], long n, int lo_bit, int hi_bit,
+                        int nonzero_flag, cudaStream_t stream, uint32_t **sorted_perm, int *launches)
+{
+    const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
+    if (n_tiles == 0) { *sorted_perm = perm[0]; return 0; }
+    if (n_tiles > s.n_tiles_capacity) return -1;
+    int cur = 0;
+    bool first = true;
+    for (int shift = lo_bit; shift < hi_bit; shift += 8) {
+        const int bits = std::min(8, hi_bit - shift);
+        const uint32_t mask = (1u << bits) - 1u;
+        sort_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(key[cur], n, shift, mask, nonzero_flag, s.tile_hist, n_tiles);
+        sort_scan_kernel<<<1, 1024, 0, stream>>>(s.tile_hist, (long)n_tiles * kRadix);
+        sort_scatter_kernel<<<n_tiles, kSortThreads, 0, stream>>>(key[cur], first ? nullptr : perm[cur], key[cur ^ 1],
+                                                                  perm[cur ^ 1], n, shift, mask, nonzero_flag,
+                                                                  s.tile_hist, n_tiles);
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        *launches += 3;
+        cur ^= 1;
+        first = false;
+    }
+    *sorted_perm = perm[cur];
+    return 0;
+}
+
+}  // namespace xs
