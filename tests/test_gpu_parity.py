@@ -1,0 +1,242 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (include/xs_gpu.h).
+
+Bars (BASELINE.json north_star): verification sums BIT-EXACT (integers derived from argmax);
+macro_xs vectors within 1e-12 relative of the oracle (summation order differs: warp
+reductions); sampled energies/materials bit-exact.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import xsbench_b200 as xs
+from xsbench_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12          # north_star tolerance for macro_xs
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+GRIDS = {"unionized": 0, "nuclide": 1, "hash": 2}
+NTHREADS = os.cpu_count() or 1
+
+
+def unhex(xs_):
+    return np.array([float.fromhex(x) for x in xs_])
+
+
+class Problem:
+    def __init__(self, size="small", n_gp=1000, grid="unionized", hb=500, **kw):
+        self.inp = xs.make_inputs(size=size, grid=grid, gridpoints=n_gp, hash_bins=hb, **kw)
+        self.sd = xs.grid_init_do_not_profile(self.inp)
+        self.gpu = xs.move_simulation_data_to_device(self.inp, self.sd)
+        self.oracle = ol.OracleProblem(self.inp.n_isotopes, n_gp, GRIDS[grid], hb)
+
+    def close(self):
+        self.gpu.release()
+        xs.free_simulation_data(self.sd)
+        self.oracle.close()
+
+
+@pytest.fixture(scope="module", params=["unionized", "hash", "nuclide"])
+def small(request):
+    p = Problem("small", 1000, request.param, 500, method="event", lookups=100000)
+    yield p
+    p.close()
+
+
+def max_rel(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+# ---- event mode, every kernel variant -----------------------------------------------------------
+@pytest.mark.parametrize("kernel_id", [0, 1, 2, 3, 4, 5, 6])
+def test_event_checksum_all_variants(small, kernel_id):
+    inp = xs.make_inputs(size="small", grid={0: "unionized", 1: "nuclide", 2: "hash"}[small.inp.grid_type],
+                         gridpoints=1000, hash_bins=500, method="event", lookups=100000, kernel_id=kernel_id)
+    res = small.gpu.run(inp)
+    assert res.n_lookups == 100000
+    assert res.verification == 302880                      # golden, from the unmodified reference
+    assert res.verification == small.oracle.event(0, 100000, NTHREADS)
+    assert res.gpu_launches >= 1 and res.device_seconds > 0
+
+
+def test_event_per_lookup_parity(small):
+    n = 20000
+    e, m, macro, am = small.gpu.dump(0, n)
+    v, oe, om, omacro, oam = small.oracle.event_dump(0, n)
+    assert np.array_equal(e, oe), "sampled energies must be bit-exact"
+    assert np.array_equal(m, om), "sampled materials must be bit-exact"
+    assert np.array_equal(am, oam), "argmax indices must be bit-exact"
+    assert max_rel(macro, omacro) <= REL_TOL
+    assert set(np.unique(m)) == set(range(12))
+
+
+def test_event_golden_rows(small):
+    """Committed vectors from the unmodified reference (incl. ids far into the stream)."""
+    for g in GOLDEN["lookups"]:
+        if (g["n_isotopes"], g["n_gridpoints"], g["grid_type"]) != (68, 1000, small.inp.grid_type):
+            continue
+        for row in g["rows"]:
+            e, m, macro, am = small.gpu.dump(row["id"], 1)
+            assert e[0] == float.fromhex(row["energy"]) and m[0] == row["mat"] and am[0] == row["argmax"]
+            assert max_rel(macro[0], unhex(row["macro_xs"])) <= REL_TOL
+
+
+def test_run_range_partition_is_exact(small):
+    whole = small.gpu.run_range(0, 50001).verification
+    parts = [small.gpu.run_range(a, b - a) for a, b in ((0, 1), (1, 32), (32, 33), (33, 20000), (20000, 50001))]
+    assert sum(p.verification for p in parts) == whole == small.oracle.event(0, 50001, NTHREADS)
+    assert sum(p.n_lookups for p in parts) == 50001
+    far = small.gpu.run_range(900_000_000, 1000)           # ids near 2^30: 64-bit ids on the device
+    assert far.verification == small.oracle.event(900_000_000, 1000, NTHREADS)
+    empty = small.gpu.run_range(5, 0)
+    assert empty.verification == 0 and empty.n_lookups == 0
+
+
+# ---- host-sample entry point (edge cases) ----------------------------------------------------------
+def test_lookup_samples_matches_oracle(small):
+    rng = np.random.default_rng(11)
+    grid_e = small.oracle.nuclide_grid[0::6]
+    e = np.concatenate([rng.random(5000),
+                        [0.0, 5e-324, 1e-300, 1e-12, 0.5, 1.0 - 2.0**-53],        # range extremes
+                        grid_e[:40], np.nextafter(grid_e[:40], 0), np.nextafter(grid_e[:40], 1),   # on / around grid points
+                        [grid_e.min(), grid_e.max(), np.nextafter(grid_e.max(), 1)]])
+    m = rng.integers(0, 12, len(e)).astype(np.int32)
+    res, macro = small.gpu.lookup_samples(e, m, want_macro_xs=True)
+    v, omacro = small.oracle.lookup_samples(e, m)
+    assert res.verification == v and res.n_lookups == len(e)
+    assert max_rel(macro, omacro) <= REL_TOL
+    assert res.h2d_bytes == len(e) * 12 and res.d2h_bytes >= len(e) * 40
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1000])
+def test_lookup_samples_ragged_sizes(small, n):
+    rng = np.random.default_rng(n)
+    e, m = rng.random(n), rng.integers(0, 12, n).astype(np.int32)
+    res, macro = small.gpu.lookup_samples(e, m, want_macro_xs=True)
+    v, omacro = small.oracle.lookup_samples(e, m) if n else (0, np.empty((0, 5)))
+    assert res.verification == v and res.n_lookups == n
+    if n:
+        assert max_rel(macro, omacro) <= REL_TOL
+
+
+@pytest.mark.parametrize("mat", [0, 2, 4, 11])
+def test_lookup_samples_single_material(small, mat):
+    rng = np.random.default_rng(mat)
+    e = rng.random(3000); m = np.full(3000, mat, np.int32)
+    res, macro = small.gpu.lookup_samples(e, m, want_macro_xs=True)
+    v, omacro = small.oracle.lookup_samples(e, m)
+    assert res.verification == v and max_rel(macro, omacro) <= REL_TOL
+
+
+def test_results_are_reproducible_run_to_run(small):
+    a = small.gpu.dump(0, 4096)[2]
+    b = small.gpu.dump(0, 4096)[2]
+    assert np.array_equal(a, b)          # fixed reduction tree => bitwise deterministic
+
+
+# ---- history mode (CPU-only in the reference: openmp-threading/Simulation.c:116-238) -------------------
+@pytest.mark.parametrize("grid,hb", [("unionized", 10000), ("hash", 500), ("nuclide", 10000)])
+def test_history_mode(grid, hb):
+    p = Problem("small", 1000, grid, hb, method="history", lookups=34, particles=3000)
+    try:
+        res = p.gpu.run()
+        assert res.n_lookups == 34 * 3000
+        assert res.verification == 309181                   # golden (reference), grid-type invariant
+        assert res.verification == p.oracle.history(0, 3000, 34, NTHREADS)
+        part = p.gpu.run_range(1000, 500)
+        assert part.verification == p.oracle.history(1000, 500, 34, NTHREADS)
+        short = xs.make_inputs(size="small", grid=grid, gridpoints=1000, hash_bins=hb, method="history", lookups=7, particles=900)
+        assert p.gpu.run(short).verification == p.oracle.history(0, 900, 7, NTHREADS)
+    finally:
+        p.close()
+
+
+# ---- the large fuel (321 nuclides) at reduced grid size -------------------------------------------
+@pytest.mark.parametrize("grid,hb", [("unionized", 10000), ("hash", 2000)])
+def test_large_fuel_small_grid(grid, hb):
+    p = Problem("large", 1000, grid, hb, method="event", lookups=100000)
+    try:
+        assert p.gpu.run().verification == 303045           # golden (reference)
+        for k in (4, 6):
+            inp = xs.make_inputs(size="large", grid=grid, gridpoints=1000, hash_bins=hb, method="event", lookups=100000, kernel_id=k)
+            assert p.gpu.run(inp).verification == 303045
+        e, m, macro, am = p.gpu.dump(0, 5000)
+        _, oe, om, omacro, oam = p.oracle.event_dump(0, 5000)
+        assert np.array_equal(e, oe) and np.array_equal(m, om) and np.array_equal(am, oam)
+        assert max_rel(macro, omacro) <= REL_TOL
+        for g in GOLDEN["lookups"]:
+            if (g["n_isotopes"], g["n_gridpoints"], g["grid_type"]) == (355, 1000, p.inp.grid_type):
+                for row in g["rows"]:
+                    _, _, x, a = p.gpu.dump(row["id"], 1)
+                    assert a[0] == row["argmax"] and max_rel(x[0], unhex(row["macro_xs"])) <= REL_TOL
+    finally:
+        p.close()
+
+
+# ---- both gather mappings give the same integers -----------------------------------------------------
+def test_gather_variants_agree(monkeypatch):
+    sums = []
+    for gather in ("0", "1"):
+        monkeypatch.setenv("XSB200_GATHER", gather)
+        p = Problem("small", 1000, "unionized", 500, method="event", lookups=50000)
+        try:
+            sums.append(p.gpu.run().verification)
+            e, m, macro, am = p.gpu.dump(0, 3000)
+            assert max_rel(macro, p.oracle.event_dump(0, 3000)[3]) <= REL_TOL
+        finally:
+            p.close()
+    assert sums[0] == sums[1] == ol.OracleProblem(68, 1000, 0, 500).event(0, 50000, NTHREADS)
+
+
+# ---- error behaviour: status codes, never exit() ------------------------------------------------------
+def test_error_codes(small):
+    bad_k = xs.make_inputs(size="small", gridpoints=1000, method="event", lookups=10, kernel_id=7,
+                           grid={0: "unionized", 1: "nuclide", 2: "hash"}[small.inp.grid_type], hash_bins=500)
+    with pytest.raises(xs.XSGpuError) as ei:            # reference: "No kernel ID" + exit(1), cuda/Main.cu:78-82
+        small.gpu.run(bad_k)
+    assert ei.value.code == _abi.XS_ERR_ARG
+    other = xs.make_inputs(size="small", gridpoints=999, method="event", lookups=10)
+    with pytest.raises(xs.XSGpuError):
+        small.gpu.run(other)
+    with pytest.raises(xs.XSGpuError):
+        small.gpu.run_range(-1, 5)
+
+
+# ---- official table at full size ------------------------------------------------------------------------
+@pytest.mark.slow
+def test_official_small_event_full_size():
+    p = Problem("small", 11303, "unionized", 10000, method="event")
+    try:
+        assert p.inp.lookups == 17_000_000
+        for k in (0, 6):
+            inp = xs.make_inputs(size="small", method="event", kernel_id=k)
+            res = p.gpu.run(inp)
+            assert res.checksum == 945990 and res.n_lookups == 17_000_000
+        hist = xs.make_inputs(size="small", method="history")
+        assert p.gpu.run(hist).checksum == 941535
+    finally:
+        p.close()
+
+
+@pytest.mark.slow
+def test_official_large_event_full_size():
+    """The canonical FOM configuration (BASELINE.json configs[1]): 355 nuclides, 5.6 GB."""
+    inp = xs.make_inputs(size="large", method="event")
+    sd = xs.grid_init_do_not_profile(inp)
+    gpu = xs.move_simulation_data_to_device(inp, sd)
+    xs.free_simulation_data(sd)
+    try:
+        for k in (0, 1, 4, 6):
+            res = gpu.run(xs.make_inputs(size="large", method="event", kernel_id=k))
+            assert res.checksum == 952131, k
+            assert res.n_lookups == 17_000_000
+        # size-independent property: any partition of the id range sums to the whole
+        a = gpu.run_range(0, 6_000_000).verification + gpu.run_range(6_000_000, 11_000_000).verification
+        assert a % 999983 == 952131
+        assert gpu.run(xs.make_inputs(size="large", method="history")).checksum == 954318
+    finally:
+        gpu.release()
