@@ -14,7 +14,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-GPU_LIB_PATH = os.path.join(PKG_DIR, "libxsb200.so")
+GPU_LIB_PATH = os.environ.get("XSB200_GPU_LIB") or os.path.join(PKG_DIR, "libxsb200.so")   # override: experiments only
 HOST_LIB_PATH = os.path.join(PKG_DIR, "libxsb200_host.so")
 
 # constants (include/xs_gpu.h)

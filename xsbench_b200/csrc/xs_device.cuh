@@ -35,6 +35,8 @@ struct Problem {
     const double2 *grid;         // nuclide grid viewed as 16-byte chunks: point = 3 chunks
                                  //   chunk0 = (energy,total) chunk1 = (elastic,absorbtion)
                                  //   chunk2 = (fission,nu_fission)
+    const double2 *pairs;        // pair records (see xs_build_pairs_kernel): 8 chunks = 128 B per
+                                 //   (nuclide, k): low point k and high point k+1 interleaved
     const uint32_t *ueg_bucket;  // [n_buckets+1]      bucket -> first UEG row in it
     const int     *mat_first;    // [13]  CSR offsets of the compact material table
     const int     *mat_nuc;      // [mat_first[12]]    nuclide id
@@ -49,6 +51,8 @@ struct Problem {
 };
 
 __constant__ double c_mat_threshold[kNumMaterials];
+constexpr int kMaxConstConc = 1024;
+__constant__ double c_mat_conc[kMaxConstConc];      // copy of Problem::mat_conc (uniform-datapath reads)
 
 // ---------------------------------------------------------------------------------------
 // LCG: x <- (a x + 1) mod 2^63
@@ -90,59 +94,89 @@ XS_DEV int pick_material(double roll)
 // ---------------------------------------------------------------------------------------
 // Loads.  Read-only (.nc) path; eviction-priority hints keep the small, hot search
 // structures in L2 while the 5.7 GB index grid streams through.
+//
+// Measured on B200 (profiles/r01_notes.md): ".L1::no_allocate" makes a load evict_first in
+// L2 as well.  With it on the nuclide-grid loads the 192 MB grid never stayed in the 126 MB
+// L2 (hit rate 27 %, 162 GB of DRAM reads per run, DRAM-bound); the grid loads therefore use
+// the default policy (L1 allocate, L2 evict_normal) and only the index rows are streamed.
 // ---------------------------------------------------------------------------------------
-XS_DEV double2 ldg_grid(const double2 *p)
-{
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-                 : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-XS_DEV double ldg_grid_energy(const double2 *p)
-{
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-// L2 eviction-priority policies (createpolicy): evict_last for the small hot search
-// structures, evict_first for the streamed index-grid rows.  On sm_100a the bare
-// ".L2::evict_*" qualifier exists only for 256-bit loads; narrower loads take a policy
-// operand through ".L2::cache_hint".
-XS_DEV uint64_t policy_keep()
+#ifndef XS_GRID_LOAD
+#define XS_GRID_LOAD 0
+#endif
+XS_DEV uint64_t policy_keep_grid()
 {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+XS_DEV double2 ldg_grid(const double2 *p)
+{
+    double2 v;
+#if XS_GRID_LOAD == 0
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#elif XS_GRID_LOAD == 1      // coherent path, default policy (what the reference's loads compile to)
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#elif XS_GRID_LOAD == 2      // read-only path + explicit L2 evict_last
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy_keep_grid()));
+#elif XS_GRID_LOAD == 3      // coherent path + explicit L2 evict_last
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy_keep_grid()));
+#elif XS_GRID_LOAD == 4      // plain C++ load (compiler's choice)
+    v = *p;
+#endif
+    return v;
+}
+// One 32-byte half-record: (low.chunk, high.chunk) of a pair record; 256-bit load (sm_100+).
+XS_DEV void ldg_pair(const double2 *p, double2 &lo, double2 &hi)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(lo.x), "=d"(lo.y), "=d"(hi.x), "=d"(hi.y) : "l"(p));
+}
+XS_DEV double ldg_grid_energy(const double2 *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// L2 eviction-priority policy (createpolicy).  On sm_100a the bare ".L2::evict_*" qualifier
+// exists only for 256-bit loads; narrower loads take a policy operand via ".L2::cache_hint".
+//
+// What is worth keeping in the 126 MB L2 is the 192 MB nuclide grid (96 B per nuclide and
+// lookup, ~200 sectors per lookup).  Everything else is touched once per lookup -- one
+// index-grid row segment, one bucket entry, 1-2 UEG entries -- and is loaded evict_first so it
+// does not displace grid lines.  (Measured: pinning bucket table + UEG (40 MB) with evict_last
+// left so little L2 for the grid that its hit rate fell to ~25 % and the kernel became
+// DRAM-bound at 122 GB per run; see profiles/r01_notes.md.)
 XS_DEV uint64_t policy_stream()
 {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-XS_DEV int ldg_index_stream(const int *p)         // index grid row: touched once, stream it
+XS_DEV int ldg_index_stream(const int *p)         // unionized index row: touched once
 {
     int v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
                  : "=r"(v) : "l"(p), "l"(policy_stream()));
     return v;
 }
-XS_DEV int ldg_index_keep(const int *p)           // hash grid: 13.5 MiB, keep it in L2
+XS_DEV int ldg_index_keep(const int *p)           // hash grid (13.5 MiB, 2 reads per nuclide): default policy
 {
     int v;
-    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy_keep()));
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-XS_DEV double ldg_keep_f64(const double *p)
+XS_DEV double ldg_search_f64(const double *p)       // UEG probe: touched once per lookup
 {
     double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy_keep()));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+                 : "=d"(v) : "l"(p), "l"(policy_stream()));
     return v;
 }
-XS_DEV uint32_t ldg_keep_u32(const uint32_t *p)
+XS_DEV uint32_t ldg_search_u32(const uint32_t *p)   // bucket table entry: touched once per lookup
 {
     uint32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy_keep()));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
+                 : "=r"(v) : "l"(p), "l"(policy_stream()));
     return v;
 }
 
@@ -162,14 +196,14 @@ XS_DEV int bucket_of(double e, double scale, int n_buckets)
 XS_DEV long ueg_row(const Problem &P, double e)
 {
     const int b = bucket_of(e, P.bucket_scale, P.n_buckets);
-    long lo = ldg_keep_u32(P.ueg_bucket + b);          // rows [lo, hi) are in bucket b
-    long hi = ldg_keep_u32(P.ueg_bucket + b + 1);
+    long lo = ldg_search_u32(P.ueg_bucket + b);          // rows [lo, hi) are in bucket b
+    long hi = ldg_search_u32(P.ueg_bucket + b + 1);
     // upper_bound within [lo, hi): first row with ueg > e
     while (hi - lo > 4) {
         const long mid = lo + (hi - lo) / 2;
-        if (ldg_keep_f64(P.ueg + mid) > e) hi = mid; else lo = mid + 1;
+        if (ldg_search_f64(P.ueg + mid) > e) hi = mid; else lo = mid + 1;
     }
-    while (lo < hi && !(ldg_keep_f64(P.ueg + lo) > e)) lo++;
+    while (lo < hi && !(ldg_search_f64(P.ueg + lo) > e)) lo++;
     long row = lo - 1;
     if (row < 0) row = 0;
     if (row > P.n_ueg - 2) row = P.n_ueg - 2;
@@ -227,6 +261,13 @@ XS_DEV long locate(const Problem &P, double e)
     if (GRID == kUnionized) return ueg_row(P, e);
     if (GRID == kHash)      return hash_bin(P, e);
     return -1;
+}
+
+XS_DEV long locate_rt(const Problem &P, int grid_type, double e)
+{
+    if (grid_type == kUnionized) return ueg_row(P, e);
+    if (grid_type == kHash)      return hash_bin(P, e);
+    return 0;
 }
 
 // hi - f*(hi - lo), f = (hi.E - E)/(hi.E - lo.E)

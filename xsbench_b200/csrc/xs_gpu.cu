@@ -55,6 +55,8 @@ int env_int(const char *name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// device counters: [0,16) batch counters of the event kernel, [16,32) partition cursors
+enum { kNumCounters = 32, kCursorBase = 16 };
 enum { EV_START = 0, EV_SAMPLED, EV_SORTED, EV_LOOKED_UP, EV_DONE, EV_COUNT };
 
 struct DeviceState {
@@ -74,7 +76,7 @@ struct DeviceState {
     size_t resident_bytes = 0;
     // per-run scratch
     unsigned long long *accum = nullptr;   // device [2]
-    unsigned int *counters = nullptr;      // device [16]: batch counters
+    unsigned int *counters = nullptr;      // device [kNumCounters]
     unsigned int *histogram = nullptr;     // device [16]
     unsigned long long *h_accum = nullptr; // pinned host [2]
     unsigned int *h_hist = nullptr;        // pinned host [16]
@@ -83,6 +85,13 @@ struct DeviceState {
     int *samp_mat = nullptr;
     uint32_t *key[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     xs::SortScratch sort{};
+    double2 *pairs = nullptr;              // pair records for the window kernel (128 B per grid point)
+    uint32_t *samp_where = nullptr;        // [sample_capacity] UEG row / hash bin per sample
+    double *grp_e = nullptr;               // samples grouped by material: energy,
+    uint32_t *grp_where = nullptr;         //   row / bin,
+    int *grp_mat = nullptr;                //   material (fuel/other partition only),
+    uint32_t *grp_id = nullptr;            //   original sample index
+    double2 *sweep_partial = nullptr;      // [sample_capacity*3] partial sums between windows
     double *dump_macro = nullptr;          // staging for macro_xs output
     long dump_capacity = 0;
     cudaEvent_t ev[EV_COUNT] = {};
@@ -99,6 +108,10 @@ struct xs_gpu_ctx {
     long n_ueg = 0;
     int gather = xs::kTriple;
     int blocks_per_sm = 0;                 // 0 = from occupancy
+    int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
+    int window = 40;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
+    int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
+    int num_nucs[XS_NUM_MATERIALS] = {};
     size_t smem_bytes = 0;
     void *nccl = nullptr;                  // multi-GPU collective state (xs_multi.cuh)
 };
@@ -124,6 +137,14 @@ EventKernel event_kernel(int grid, int gather)
     return table[grid][gather];
 }
 
+typedef void (*WindowKernel)(const xs::Problem, const xs::WindowArgs, const xs::BatchSink);
+WindowKernel window_kernel(int grid)
+{
+    using namespace xs;
+    static const WindowKernel table[3] = { xs_window_kernel<kUnionized>, xs_window_kernel<kNuclide>, xs_window_kernel<kHash> };
+    return table[grid];
+}
+
 HistoryKernel history_kernel(int grid, int gather)
 {
     using namespace xs;
@@ -135,12 +156,12 @@ HistoryKernel history_kernel(int grid, int gather)
     return table[grid][gather];
 }
 
-int persistent_grid(const xs_gpu_ctx *ctx, const DeviceState &d, const void *kernel, int *blocks)
+int persistent_grid(const xs_gpu_ctx *ctx, const DeviceState &d, const void *kernel, int *blocks, long smem = -1)
 {
+    const size_t dyn_smem = smem < 0 ? ctx->smem_bytes : (size_t)smem;
     int per_sm = ctx->blocks_per_sm;
     if (per_sm <= 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, xs::kBlockThreads,
-                                                               ctx->smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, xs::kBlockThreads, dyn_smem));
         if (per_sm < 1) per_sm = 1;
     }
     *blocks = per_sm * d.sm_count;
@@ -180,6 +201,13 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     CUDA_TRY(copy_in(d.grid, sd->nuclide_grid, peer ? peer->grid : nullptr, grid_bytes));
     d.resident_bytes += grid_bytes;
     P.grid = d.grid;
+    // pair records (B200 layout for the windowed sweep): one 128-byte line per (nuclide, k)
+    const size_t pair_bytes = (size_t)n_points * 8 * sizeof(double2);
+    CUDA_TRY(cudaMalloc(&d.pairs, pair_bytes));
+    xs::xs_build_pairs_kernel<<<d.sm_count * 16, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, d.pairs);
+    CUDA_TRY(cudaGetLastError());
+    d.resident_bytes += pair_bytes;
+    P.pairs = d.pairs;
 
     // search structures
     if (ctx->grid_type == XS_UNIONIZED) {
@@ -251,20 +279,23 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         thr[i] = acc;
     }
     CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_mat_threshold, thr, sizeof thr, 0, cudaMemcpyHostToDevice, d.stream));
+    if (total > xs::kMaxConstConc)
+        return set_error(XS_ERR_UNSUPP, "material table has %d entries, more than the %d this build supports", total, xs::kMaxConstConc);
+    CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_mat_conc, conc.data(), (size_t)total * sizeof(double), 0, cudaMemcpyHostToDevice, d.stream));
 
     // run scratch
     CUDA_TRY(cudaMalloc(&d.accum, 2 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&d.counters, 16 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&d.counters, kNumCounters * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&d.histogram, 16 * sizeof(unsigned int)));
     CUDA_TRY(cudaMallocHost(&d.h_accum, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&d.h_hist, 16 * sizeof(unsigned int)));
 
     CUDA_TRY(cudaStreamSynchronize(d.stream));   // host vectors above go out of scope
 
-    // L2 residency for the hot search structures (bucket table + UEG, or the hash grid):
-    // a persisting access-policy window on this stream.  The per-load evict_last /
-    // evict_first hints in xs_device.cuh work with or without it.
-    if (d.hot_slab && env_int("XSB200_L2_WINDOW", 1)) {
+    // Optional (XSB200_L2_WINDOW=1, off by default): persisting access-policy window over the
+    // search structures (bucket table + UEG, or the hash grid).  Measured on B200 it does not
+    // pay: the L2 is better spent on the nuclide grid (see the policy note in xs_device.cuh).
+    if (d.hot_slab && env_int("XSB200_L2_WINDOW", 0)) {
         size_t want = std::min<size_t>(d.hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
         if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             cudaStreamAttrValue attr;
@@ -287,6 +318,10 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
     if (n > d.sample_capacity) {
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); d.key[i] = d.perm[i] = nullptr; }
+        cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
+        cudaFree(d.sweep_partial);
+        d.samp_where = nullptr; d.grp_e = nullptr; d.grp_where = nullptr; d.grp_mat = nullptr; d.grp_id = nullptr;
+        d.sweep_partial = nullptr;
         d.samp_e = nullptr; d.samp_mat = nullptr;
         CUDA_TRY(cudaMalloc(&d.samp_e, (size_t)n * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.samp_mat, (size_t)n * sizeof(int)));
@@ -297,6 +332,13 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
             CUDA_TRY(cudaMalloc(&d.key[i], (size_t)d.sample_capacity * sizeof(uint32_t)));
             CUDA_TRY(cudaMalloc(&d.perm[i], (size_t)d.sample_capacity * sizeof(uint32_t)));
         }
+        const size_t cap = (size_t)d.sample_capacity;
+        CUDA_TRY(cudaMalloc(&d.samp_where, cap * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d.grp_e, cap * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&d.grp_where, cap * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d.grp_mat, cap * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&d.grp_id, cap * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d.sweep_partial, cap * 3 * sizeof(double2)));
         int rc = xs::sort_scratch_alloc(d.sort, d.sample_capacity);
         if (rc != 0) return set_error(XS_ERR_CUDA, "sort scratch allocation failed");
     }
@@ -335,15 +377,104 @@ int launch_event(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs
     return XS_OK;
 }
 
-int launch_sample(DeviceState &d, long first_id, long count, bool with_key, bool with_hist)
+// Windowed nuclide sweep over the lookups of one material: slots [offset, offset+count) of the
+// grouped arrays (grp_e / grp_where / id); one launch per nuclide window, see xs_window_kernel.
+int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const uint32_t *id, long offset, long count, int mat,
+                 xs::BatchSink sink)
+{
+    if (count <= 0) return XS_OK;
+    const int n_nuclides = ctx->num_nucs[mat];
+    WindowKernel k = window_kernel(ctx->grid_type);
+    int blocks = 0;
+    int rc = persistent_grid(ctx, d, (const void *)k, &blocks, 0);
+    if (rc != XS_OK) return rc;
+    const long groups = (count + xs::kSweepSlots - 1) / xs::kSweepSlots;
+    const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+    if (blocks > max_useful) blocks = (int)max_useful;
+    const int passes = (n_nuclides + ctx->window - 1) / ctx->window;
+    const int width = (n_nuclides + passes - 1) / passes;          // balanced windows
+    for (int p = 0; p < passes; p++) {
+        xs::WindowArgs a{};
+        a.energy = d.grp_e;
+        a.where = d.grp_where;
+        a.sample_id = id;
+        a.partial = d.sweep_partial;
+        a.offset = offset;
+        a.count = count;
+        a.mat = mat;
+        a.j_begin = p * width;
+        a.j_end = std::min(n_nuclides, (p + 1) * width);
+        a.first_window = p == 0;
+        a.last_window = p == passes - 1;
+        k<<<blocks, xs::kBlockThreads, 0, d.stream>>>(d.P, a, sink);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
+    }
+    return XS_OK;
+}
+
+int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bool with_where, bool with_key,
+                  bool with_hist)
 {
     int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
-    xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(first_id, count, d.samp_e, d.samp_mat,
+    xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_id, count, d.samp_e, d.samp_mat,
+                                                       with_where ? d.samp_where : nullptr,
                                                        with_key ? d.key[0] : nullptr,
                                                        with_hist ? d.histogram : nullptr);
     CUDA_TRY(cudaGetLastError());
     d.launches++;
     return XS_OK;
+}
+
+// Sorted variants on device-resident samples (samp_e / samp_mat / samp_where / histogram and,
+// for -k 6, key[0] are ready): regroup, then sweep material by material.
+int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long count, xs::BatchSink sink)
+{
+    int rc = XS_OK;
+    const uint32_t *id = nullptr;
+    if (kernel_id == 6) {
+        // optimization 6 (cuda/Simulation.cu:1024-1099): sort by (material, energy)
+        uint32_t *sorted_perm = nullptr;
+        rc = xs::sort_lookups(d.sort, d.key, d.perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
+        if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+        const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
+        xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e, d.samp_where, count, d.grp_e, d.grp_where);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
+        id = sorted_perm;
+    } else {
+        // optimization 4 (:754-821): group by material; optimization 5 (:895-958): fuel first
+        const int tiles = (int)((count + 256 * xs::kPartItems - 1) / (256 * xs::kPartItems));
+        xs::xs_partition_kernel<<<tiles, 256, 0, d.stream>>>(d.samp_e, d.samp_mat, d.samp_where, count, d.histogram,
+                                                           d.counters + kCursorBase, kernel_id == 5, d.grp_e, d.grp_where,
+                                                           kernel_id == 5 ? d.grp_mat : nullptr, d.grp_id);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
+        id = d.grp_id;
+    }
+    CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+    // group sizes: the sampler's histogram (device -> pinned host; the launches below need them)
+    CUDA_TRY(cudaMemcpyAsync(d.h_hist, d.histogram, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    long offset = 0;
+    if (kernel_id == 5) {
+        const long n_fuel = d.h_hist[0];
+        rc = launch_sweep(ctx, d, id, 0, n_fuel, 0, sink);
+        if (rc == XS_OK && count > n_fuel) {
+            xs::BatchSource rest{};
+            rest.energy = d.grp_e + n_fuel;
+            rest.mat = d.grp_mat + n_fuel;
+            rest.count = count - n_fuel;
+            rest.mat_lo = 0; rest.mat_hi = XS_NUM_MATERIALS - 1;
+            rc = launch_event(ctx, d, rest, sink, 1);
+        }
+        return rc;
+    }
+    for (int m = 0; m < XS_NUM_MATERIALS && rc == XS_OK; m++) {
+        rc = launch_sweep(ctx, d, id, offset, d.h_hist[m], m, sink);
+        offset += d.h_hist[m];
+    }
+    return rc;
 }
 
 // One device's share of an event-mode run: ids [first_id, first_id + count).
@@ -353,7 +484,7 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
     d.launches = 0;
     CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
     CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaMemsetAsync(d.histogram, 0, 16 * sizeof(unsigned int), d.stream));
 
     xs::BatchSink sink{};
@@ -373,7 +504,7 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
     } else {
         const bool sorted = kernel_id == 4 || kernel_id == 5 || kernel_id == 6;
         if ((rc = ensure_sample_buffers(d, count, sorted)) != XS_OK) return rc;
-        if ((rc = launch_sample(d, first_id, count, sorted, sorted)) != XS_OK) return rc;
+        if ((rc = launch_sample(ctx, d, first_id, count, sorted, kernel_id == 6, sorted)) != XS_OK) return rc;
         CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
         src.energy = d.samp_e;
         src.mat = d.samp_mat;
@@ -396,36 +527,7 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
                 if (rc == XS_OK) rc = launch_event(ctx, d, src, sink, 1);
             }
         } else {
-            // optimizations 4/5/6 (:754-821, :895-958, :1024-1099): reorder the lookups with
-            // the hand-written radix sort, then launch per contiguous material range.
-            //   4: key = material            (4 bits)
-            //   5: key = fuel / not fuel     (1 bit; the partition the reference intended)
-            //   6: key = material | energy   (32 bits)
-            int key_lo_bit = 28, key_hi_bit = 32;
-            if (kernel_id == 6) key_lo_bit = 0;
-            uint32_t *sorted_perm = nullptr;
-            int src_is_fuel_bit = (kernel_id == 5);
-            rc = xs::sort_lookups(d.sort, d.key, d.perm, count, key_lo_bit, key_hi_bit,
-                                  src_is_fuel_bit, d.stream, &sorted_perm, &d.launches);
-            if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
-            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
-            // per-material counts were produced by the sampling kernel
-            CUDA_TRY(cudaMemcpyAsync(d.h_hist, d.histogram, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
-            CUDA_TRY(cudaStreamSynchronize(d.stream));
-            long offset = 0;
-            const int n_groups = (kernel_id == 5) ? 2 : XS_NUM_MATERIALS;
-            for (int g = 0; g < n_groups && rc == XS_OK; g++) {
-                long n_g = 0;
-                if (kernel_id == 5) {
-                    if (g == 0) n_g = d.h_hist[0];
-                    else for (int m = 1; m < XS_NUM_MATERIALS; m++) n_g += d.h_hist[m];
-                } else n_g = d.h_hist[g];
-                xs::BatchSource part = src;
-                part.perm = sorted_perm + offset;
-                part.count = n_g;
-                rc = launch_event(ctx, d, part, sink, g);
-                offset += n_g;
-            }
+            rc = enqueue_grouped_lookup(ctx, d, kernel_id, count, sink);
         }
     }
     if (rc != XS_OK) return rc;
@@ -439,7 +541,7 @@ int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n
     d.launches = 0;
     CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
     CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
     CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
     if (n_particles > 0) {
@@ -545,6 +647,10 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->n_ueg = in->grid_type == XS_UNIONIZED ? sd->length_unionized_energy_array : 0;
     ctx->gather = env_int("XSB200_GATHER", xs::kTriple) ? xs::kTriple : xs::kLanePerNuclide;
     ctx->blocks_per_sm = env_int("XSB200_BLOCKS_PER_SM", 0);
+    ctx->sweep = env_int("XSB200_SWEEP", 1);
+    ctx->window = std::max(1, env_int("XSB200_WINDOW", 40));
+    ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
+    for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);
     for (int g = 0; g < n_gpus; g++) ctx->dev[g].device = dev0 + g;
 
@@ -634,7 +740,7 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
         CUDA_TRY(cudaMemcpyAsync(d.samp_mat, h_mat + lo, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
         CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
-        CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
         CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
         CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
         xs::BatchSource src{};
@@ -670,7 +776,7 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
     CUDA_TRY(cudaMalloc(&d_mat, (size_t)n * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_am, (size_t)n * sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.counters, 0, 16 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     xs::BatchSource src{};
     src.first_id = first_id; src.count = n; src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
     xs::BatchSink sink{};
@@ -731,6 +837,8 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         xs::sort_scratch_free(d.sort);
+        cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
+        cudaFree(d.sweep_partial); cudaFree(d.pairs);
         cudaFree(d.dump_macro);
         if (d.h_accum) cudaFreeHost(d.h_accum);
         if (d.h_hist) cudaFreeHost(d.h_hist);

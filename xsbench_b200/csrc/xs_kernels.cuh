@@ -25,12 +25,15 @@ constexpr int kWarpsPerBlock = kBlockThreads / 32;
 constexpr double kTieGuard = 1e-10;      // relative gap below which order of summation could
                                          // change an integer decision -> settle serially
 
-// Lane mappings of the gather.
-//   kLanePerNuclide : lane j handles nuclide j (+32, ...): 6 divergent 16-B loads per lane.
-//   kTriple         : 3 adjacent lanes share one nuclide; lane c loads chunk c of the low and
-//                     of the high grid point (2 loads per lane, 48 contiguous bytes per
-//                     instruction and nuclide -> ~2.5x fewer L1 wavefronts per nuclide).
+// Gather strategies.
+//   kLanePerNuclide : every lookup by the whole warp, lane j handles nuclide j (+32, ...):
+//                     6 divergent 16-B loads per lane and round.  Simple; kept for comparison.
+//   kTriple (default, "hybrid"): small materials (n <= 32) are evaluated one lookup per lane
+//                     (phase A, lane_macro_small); big ones (fuel) by the whole warp with 3
+//                     lanes per nuclide and kBigUnroll x 10 nuclides in flight (phase B,
+//                     warp_macro_big).
 constexpr int kLanePerNuclide = 0, kTriple = 1;
+constexpr int kSmallMax = 32;            // materials with at most this many nuclides go to phase A
 
 // Where a batch's (energy, material) pairs come from.
 struct BatchSource {
@@ -101,36 +104,123 @@ XS_DEV void warp_macro_lane_per_nuclide(const Problem &P, const int *s_nuc, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Phase A of a batch: every lane evaluates ITS OWN lookup when that lookup's material is small
+// (n <= 32 nuclides: everything except fuel).  Two nuclides per iteration are in flight (12
+// 16-byte loads per lane) and the index entries of the next pair are requested before the
+// current pair is consumed.  Contributions are added in reference order j = 0,1,2,... so
+// these lookups are bit-identical to the reference.  n == 0 switches a lane off.
+// ---------------------------------------------------------------------------------------
 template <int GRID>
-XS_DEV void warp_macro_triple(const Problem &P, const int *s_nuc, const double *s_conc,
-                              int first, int n, double e, long where, int lane,
-                              double *exchange /* 8 doubles, per warp */, double out[5])
+XS_DEV void lane_macro_small(const Problem &P, const int *s_nuc, const double *s_conc, int first, int n,
+                             double e, long where, double acc[5])
+{
+#pragma unroll
+    for (int k = 0; k < 5; k++) acc[k] = 0.0;
+    const int n_max = __reduce_max_sync(kFullMask, n);
+    int nuc0 = 0, nuc1 = 0, low0 = 0, low1 = 0;
+    if (0 < n) { nuc0 = s_nuc[first];     low0 = nuclide_low<GRID>(P, e, where, nuc0); }
+    if (1 < n) { nuc1 = s_nuc[first + 1]; low1 = nuclide_low<GRID>(P, e, where, nuc1); }
+    for (int j = 0; j < n_max; j += 2) {
+        const bool on0 = j < n, on1 = j + 1 < n;
+        double2 a0, a1, a2, a3, a4, a5, b0, b1, b2, b3, b4, b5;
+        a0 = a1 = a2 = a4 = a5 = b0 = b1 = b2 = b4 = b5 = make_double2(0.0, 0.0);
+        a3 = b3 = make_double2(1.0, 0.0);
+        if (on0) {
+            const double2 *p = P.grid + 3 * ((long)nuc0 * P.n_gp + low0);
+            a0 = ldg_grid(p); a1 = ldg_grid(p + 1); a2 = ldg_grid(p + 2);
+            a3 = ldg_grid(p + 3); a4 = ldg_grid(p + 4); a5 = ldg_grid(p + 5);
+        }
+        if (on1) {
+            const double2 *p = P.grid + 3 * ((long)nuc1 * P.n_gp + low1);
+            b0 = ldg_grid(p); b1 = ldg_grid(p + 1); b2 = ldg_grid(p + 2);
+            b3 = ldg_grid(p + 3); b4 = ldg_grid(p + 4); b5 = ldg_grid(p + 5);
+        }
+        const double conc0 = on0 ? s_conc[first + j] : 0.0;
+        const double conc1 = on1 ? s_conc[first + j + 1] : 0.0;
+        // request the next two index entries before touching the data above
+        if (j + 2 < n) { nuc0 = s_nuc[first + j + 2]; low0 = nuclide_low<GRID>(P, e, where, nuc0); }
+        if (j + 3 < n) { nuc1 = s_nuc[first + j + 3]; low1 = nuclide_low<GRID>(P, e, where, nuc1); }
+        if (on0) {
+            const double f = (a3.x - e) / (a3.x - a0.x);
+            acc[0] += lerp_xs(a0.y, a3.y, f) * conc0;
+            acc[1] += lerp_xs(a1.x, a4.x, f) * conc0;
+            acc[2] += lerp_xs(a1.y, a4.y, f) * conc0;
+            acc[3] += lerp_xs(a2.x, a5.x, f) * conc0;
+            acc[4] += lerp_xs(a2.y, a5.y, f) * conc0;
+        }
+        if (on1) {
+            const double f = (b3.x - e) / (b3.x - b0.x);
+            acc[0] += lerp_xs(b0.y, b3.y, f) * conc1;
+            acc[1] += lerp_xs(b1.x, b4.x, f) * conc1;
+            acc[2] += lerp_xs(b1.y, b4.y, f) * conc1;
+            acc[3] += lerp_xs(b2.x, b5.x, f) * conc1;
+            acc[4] += lerp_xs(b2.y, b5.y, f) * conc1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Phase B: one big lookup (fuel: 321 nuclides) by the whole warp.  Three adjacent lanes share
+// a nuclide -- lane c loads 16-byte chunk c of the low and of the high grid point, so one
+// load instruction touches 48 contiguous bytes per nuclide (about 1.3 L1 wavefronts per
+// nuclide and instruction instead of 6 for one lane per nuclide).  U steps of 10 nuclides are
+// in flight per iteration (2U loads per lane) and the index entries of the next iteration are
+// requested before the current data is consumed.  e / where / (first, n) are warp-uniform;
+// on return every lane holds the same five sums.
+// ---------------------------------------------------------------------------------------
+template <int GRID, int U>
+XS_DEV void warp_macro_big(const Problem &P, const int *s_nuc, const double *s_conc, int first, int n,
+                           double e, long where, int lane, double *exchange /* 8 doubles, per warp */,
+                           double out[5])
 {
     const int slot = lane / 3;                 // 10 nuclides per step; lanes 30,31 idle
     const int chunk = lane - 3 * slot;         // which 16-byte chunk of a grid point
     const bool lane_on = lane < 30;
     const int f_src = lane - chunk;            // lane holding both energies of this slot
     double acc_x = 0.0, acc_y = 0.0;
+    long at[U];                                // chunk index of the low point, -1 = off
 
-#pragma unroll 2
-    for (int j0 = 0; j0 < n; j0 += 10) {
-        const int j = j0 + slot;
-        const bool on = lane_on && j < n;
-        double2 lo = make_double2(0.0, 0.0), hi = make_double2(1.0, 0.0);
-        double conc = 0.0;
-        if (on) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int j = u * 10 + slot;
+        at[u] = -1;
+        if (lane_on && j < n) {
             const int nuc = s_nuc[first + j];
-            conc = s_conc[first + j];
-            const int low = nuclide_low<GRID>(P, e, where, nuc);
-            const double2 *p = P.grid + 3 * ((long)nuc * P.n_gp + low) + chunk;
-            lo = ldg_grid(p);
-            hi = ldg_grid(p + 3);
+            at[u] = 3 * ((long)nuc * P.n_gp + nuclide_low<GRID>(P, e, where, nuc)) + chunk;
         }
-        const double f_own = (hi.x - e) / (hi.x - lo.x);      // meaningful on chunk 0 only
-        const double f = __shfl_sync(kFullMask, f_own, f_src);
-        if (on) {
-            acc_x += lerp_xs(lo.x, hi.x, f) * conc;
-            acc_y += lerp_xs(lo.y, hi.y, f) * conc;
+    }
+    for (int j0 = 0; j0 < n; j0 += 10 * U) {
+        double2 lo[U], hi[U];
+        double conc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            lo[u] = make_double2(0.0, 0.0);
+            hi[u] = make_double2(1.0, 0.0);
+            conc[u] = 0.0;
+            if (at[u] >= 0) {
+                lo[u] = ldg_grid(P.grid + at[u]);
+                hi[u] = ldg_grid(P.grid + at[u] + 3);
+                conc[u] = s_conc[first + j0 + u * 10 + slot];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {          // next iteration's index entries
+            const int j = j0 + 10 * U + u * 10 + slot;
+            at[u] = -1;
+            if (lane_on && j < n) {
+                const int nuc = s_nuc[first + j];
+                at[u] = 3 * ((long)nuc * P.n_gp + nuclide_low<GRID>(P, e, where, nuc)) + chunk;
+            }
+        }
+        double f[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) f[u] = (hi[u].x - e) / (hi[u].x - lo[u].x);   // used from chunk 0
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double fu = __shfl_sync(kFullMask, f[u], f_src);
+            acc_x += lerp_xs(lo[u].x, hi[u].x, fu) * conc[u];                     // conc == 0 when off
+            acc_y += lerp_xs(lo[u].y, hi[u].y, fu) * conc[u];
         }
     }
     // Sum the 10 slots: lanes 0,1,2 end up with the totals of chunk 0,1,2.
@@ -148,11 +238,13 @@ XS_DEV void warp_macro_triple(const Problem &P, const int *s_nuc, const double *
     for (int k = 0; k < 5; k++) out[k] = exchange[k + 1];
 }
 
+constexpr int kBigUnroll = 4;
+
 template <int GRID, int GATHER>
 XS_DEV void warp_macro(const Problem &P, const int *s_nuc, const double *s_conc, int first, int n,
                        double e, long where, int lane, double *exchange, double out[5])
 {
-    if (GATHER == kTriple) warp_macro_triple<GRID>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, out);
+    if (GATHER == kTriple) warp_macro_big<GRID, kBigUnroll>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, out);
     else                   warp_macro_lane_per_nuclide<GRID>(P, s_nuc, s_conc, first, n, e, where, lane, out);
 }
 
@@ -213,11 +305,18 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
         }
         const bool want = have && mat_l >= src.mat_lo && mat_l <= src.mat_hi;
         long where_l = want ? locate<GRID>(P, e_l) : 0;
-        unsigned todo = __ballot_sync(kFullMask, want);
-
-        // ---- warp-cooperative part: one lookup of the batch at a time --------------------
+        const int first_l = want ? T.first[mat_l] : 0;
+        const int n_l = want ? T.first[mat_l + 1] - first_l : 0;
         int my_argmax = 0;
         double mine[5] = {0, 0, 0, 0, 0};
+
+        // ---- phase A: small materials, one lookup per lane --------------------------------
+        const bool small_l = GATHER == kTriple && want && n_l <= kSmallMax;
+        if (GATHER == kTriple && __any_sync(kFullMask, small_l))
+            lane_macro_small<GRID>(P, s_nuc, s_conc, first_l, small_l ? n_l : 0, e_l, where_l, mine);
+
+        // ---- phase B: big materials, the whole warp on one lookup at a time ---------------
+        unsigned todo = __ballot_sync(kFullMask, want && !small_l);
         while (todo) {
             const int i = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -262,13 +361,180 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 }
 
 // ---------------------------------------------------------------------------------------
-// Sampling kernel (variants 1..6): writes energy, material and -- for the sorted variants
-// -- a sort key, and counts lookups per material.  key = (material << 28) | top 28 bits of
-// the 63-bit LCG state behind the energy (monotone in the energy).
+// Window kernel: lookups of ONE material, restricted to the nuclide window [j_begin, j_end)
+// of that material's nuclide list ("windowed nuclide sweep").
+//
+// Why: the gather is 96 B per (lookup, nuclide) at a random grid point of that nuclide.  If
+// every warp works on its own lookup front to back, the whole grid is the working set and
+// (measured, profiles/r01_notes.md) almost every pair comes from DRAM.  Here ONE LAUNCH only
+// touches the nuclides of one window, which stays resident in the 126 MB L2 while all lookups
+// of the material stream past it; DRAM only streams the index rows.  A material with more
+// nuclides than one window (fuel: 321) takes several launches; the five partial sums of a
+// lookup travel between launches through a 48-byte record in global memory (2 x 113 MB per
+// pass for fuel -- noise next to the gather).  Stream order is the only synchronisation.
+//
+// Layout: the gather reads PAIR RECORDS built once at init (xs_build_pairs_kernel): for each
+// (nuclide, k) one 128-byte-aligned record [lo.c0 hi.c0 | lo.c1 hi.c1 | lo.c2 hi.c2 | pad]
+// with c0 = (energy,total) c1 = (elastic,absorbtion) c2 = (fission,nu_fission) of grid points
+// k and k+1.  The gather of one (lookup, nuclide) is then ONE 128-byte line.
+//
+// Mapping ("transposed triple"): a warp owns 10 lookups (slots); lane c of a slot loads the
+// 32-byte third c of the slot's record with one 256-bit load -- 96 contiguous bytes per slot,
+// one L1 wavefront per slot and step (the reference-layout alternative costs 2 x 1.3).  Each
+// lane keeps the two channel sums of its chunk, accumulated in reference order j = 0,1,2,...
+// with the reference's operations, so macro_xs is bit-identical to the reference.  The record
+// numbers of the next 32 nuclides are resolved by the whole warp (coalesced index-row
+// segments) and staged in shared memory, so every index sector is requested once.
+// ---------------------------------------------------------------------------------------
+#ifndef XS_SWEEP_UNROLL
+#define XS_SWEEP_UNROLL 4
+#endif
+#ifndef XS_SWEEP_BLOCKS
+#define XS_SWEEP_BLOCKS 4
+#endif
+constexpr int kSweepUnroll = XS_SWEEP_UNROLL;
+constexpr int kSweepSlots = 10;
+
+struct WindowArgs {
+    const double   *energy;    // [.. offset+count) energies grouped by material
+    const uint32_t *where;     // same order: UEG row / hash bin
+    const uint32_t *sample_id; // same order: original sample index (only for macro_xs dumps)
+    double2        *partial;   // [3 * slots] partial sums between windows (chunk c at 3*slot + c)
+    long  offset;              // first slot of this material
+    long  count;               // lookups of this material
+    int   mat;
+    int   j_begin, j_end;      // nuclide window inside the material's list
+    int   first_window, last_window;
+};
+
+template <int GRID>
+__global__ void __launch_bounds__(kBlockThreads, XS_SWEEP_BLOCKS)
+xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
+{
+    __shared__ unsigned long long s_part[kWarpsPerBlock];
+    __shared__ uint32_t s_rec[kWarpsPerBlock][kSweepSlots][33];
+    __shared__ int s_first;
+    if (threadIdx.x == 0) s_first = P.mat_first[A.mat];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = lane / 3, chunk = lane - 3 * slot;
+    const bool lane_on = lane < 3 * kSweepSlots;
+    const int f_src = lane - chunk;
+    const int first = s_first;
+    const long n_groups = (A.count + kSweepSlots - 1) / kSweepSlots;
+    const long warp_global = (long)blockIdx.x * kWarpsPerBlock + warp;
+    const long warp_stride = (long)gridDim.x * kWarpsPerBlock;
+    unsigned long long my_sum = 0, my_count = 0;
+
+    for (long g = warp_global; g < n_groups; g += warp_stride) {
+        const long t = A.offset + g * kSweepSlots + slot;    // global slot
+        const bool on = lane_on && g * kSweepSlots + slot < A.count;
+        double e = 0.5;
+        long where = 0;
+        double acc_x = 0.0, acc_y = 0.0;
+        if (on) {
+            e = A.energy[t];
+            where = A.where[t];
+            if (!A.first_window) {
+                const double2 part = A.partial[3 * t + chunk];
+                acc_x = part.x;
+                acc_y = part.y;
+            }
+        }
+
+        for (int jb = A.j_begin; jb < A.j_end; jb += 32) {
+            const int jn = min(32, A.j_end - jb);
+            // resolve the record numbers of nuclides [jb, jb+jn) for the 10 lookups of this warp
+            __syncwarp();
+            const int my_nuc = lane < jn ? P.mat_nuc[first + jb + lane] : 0;
+#pragma unroll
+            for (int s = 0; s < kSweepSlots; s++) {
+                const long w_s = __shfl_sync(kFullMask, where, 3 * s);
+                const double e_s = __shfl_sync(kFullMask, e, 3 * s);
+                const bool slot_on = __shfl_sync(kFullMask, (int)on, 3 * s);
+                if (slot_on && lane < jn)
+                    s_rec[warp][s][lane] = (uint32_t)((long)my_nuc * P.n_gp + nuclide_low<GRID>(P, e_s, w_s, my_nuc));
+            }
+            __syncwarp();
+
+            for (int j0 = 0; j0 < jn; j0 += kSweepUnroll) {
+                double2 lo[kSweepUnroll], hi[kSweepUnroll];
+#pragma unroll
+                for (int u = 0; u < kSweepUnroll; u++) {
+                    lo[u] = make_double2(0.0, 0.0);
+                    hi[u] = make_double2(1.0, 0.0);
+                    if (on && j0 + u < jn)
+                        ldg_pair(P.pairs + 8 * (long)s_rec[warp][slot][j0 + u] + 2 * chunk, lo[u], hi[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kSweepUnroll; u++) {
+                    const double f_own = (hi[u].x - e) / (hi[u].x - lo[u].x);       // used from chunk 0
+                    const double f = __shfl_sync(kFullMask, f_own, f_src);
+                    if (j0 + u < jn) {                                              // warp-uniform
+                        const double conc = c_mat_conc[first + jb + j0 + u];
+                        if (on) {
+                            acc_x += lerp_xs(lo[u].x, hi[u].x, f) * conc;
+                            acc_y += lerp_xs(lo[u].y, hi[u].y, f) * conc;
+                        }
+                    }
+                }
+            }
+        }
+
+        if (!A.last_window) {
+            if (on) A.partial[3 * t + chunk] = make_double2(acc_x, acc_y);
+            continue;                                        // warp-uniform
+        }
+        // chunk0 = (energy, total) chunk1 = (elastic, absorbtion) chunk2 = (fission, nu_fission)
+        const double c1x = __shfl_down_sync(kFullMask, acc_x, 1), c1y = __shfl_down_sync(kFullMask, acc_y, 1);
+        const double c2x = __shfl_down_sync(kFullMask, acc_x, 2), c2y = __shfl_down_sync(kFullMask, acc_y, 2);
+        if (on && chunk == 0) {
+            const double v[5] = {acc_y, c1x, c1y, c2x, c2y};
+            double gap;
+            const int am = argmax5(v, gap);
+            my_sum += (unsigned long long)(am + 1);
+            my_count += 1;
+            if (sink.macro_out) {
+                const long id = A.sample_id ? (long)A.sample_id[t] : t;
+#pragma unroll
+                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = v[k];
+            }
+        }
+    }
+    const unsigned long long bs = block_sum(my_sum, s_part);
+    const unsigned long long bc = block_sum(my_count, s_part);
+    if (threadIdx.x == 0 && bc) {
+        atomicAdd(sink.accum, bs);
+        atomicAdd(sink.accum + 1, bc);
+    }
+}
+
+// Pair records for the window kernel (init only).  Record r = nuc*n_gp + k (k <= n_gp-2):
+//   [0]=lo.c0 [1]=hi.c0 [2]=lo.c1 [3]=hi.c1 [4]=lo.c2 [5]=hi.c2 [6],[7]=padding
+__global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp, double2 *pairs)
+{
+    const long total = n_iso * n_gp * 8;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long r = i >> 3;
+        const int q = (int)(i & 7);
+        const long k = r % n_gp;
+        double2 v = make_double2(0.0, 0.0);
+        if (q < 6 && k + 1 < n_gp) v = grid[3 * (r + (q & 1)) + (q >> 1)];
+        pairs[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Sampling kernel (variants 1..6): writes energy, material, optionally the UEG row / hash bin
+// ("where"), a sort key, and counts lookups per material (replaces 12 x thrust::count).
+// key = (material << 28) | top 28 bits of the 63-bit LCG state behind the energy (monotone in
+// the energy).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-xs_sample_kernel(long first_id, long count, double *energy, int *mat, uint32_t *key,
-                 unsigned int *mat_histogram)
+xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, double *energy, int *mat,
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -282,8 +548,10 @@ xs_sample_kernel(long first_id, long count, double *energy, int *mat, uint32_t *
         for (; t < count; t += stride) {
             const uint64_t s1 = lcg_step(s), s2 = lcg_step(s1);
             const int m = pick_material(lcg_to_double(s2));
-            energy[t] = lcg_to_double(s1);
+            const double e = lcg_to_double(s1);
+            energy[t] = e;
             mat[t] = m;
+            if (where) where[t] = (uint32_t)locate_rt(P, grid_type, e);
             if (key) key[t] = ((uint32_t)m << 28) | (uint32_t)(s1 >> 35);
             if (mat_histogram) atomicAdd(&s_hist[m], 1u);
             s = apply(hop, s);
@@ -292,6 +560,89 @@ xs_sample_kernel(long first_id, long count, double *energy, int *mat, uint32_t *
     __syncthreads();
     if (mat_histogram && threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
         atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
+}
+
+// Same bookkeeping for samples that already exist (host-provided): where + histogram.
+__global__ void __launch_bounds__(256)
+xs_locate_kernel(const Problem P, int grid_type, long count, const double *energy, const int *mat,
+                 uint32_t *where, unsigned int *mat_histogram)
+{
+    __shared__ unsigned int s_hist[kNumMaterials];
+    if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        where[t] = (uint32_t)locate_rt(P, grid_type, energy[t]);
+        atomicAdd(&s_hist[mat[t]], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
+        atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Partition by material (-k 4) or fuel / not-fuel (-k 5): replaces thrust::count x12 +
+// thrust::sort_by_key (cuda/Simulation.cu:792-797) and thrust::partition (:936).  The group
+// sizes are already known (histogram from the sampler), so one pass suffices: a block counts
+// its tile per group in shared memory, reserves a range per group with one atomicAdd on the
+// group cursor, and scatters energy / where / material / sample id.  Order inside a group is
+// arbitrary (the checksum is order independent; per-lookup outputs are addressed by id).
+// ---------------------------------------------------------------------------------------
+constexpr int kPartItems = 8;
+__global__ void __launch_bounds__(256)
+xs_partition_kernel(const double *energy, const int *mat, const uint32_t *where, long count,
+                    const unsigned int *mat_histogram, unsigned int *cursor, int fuel_or_not,
+                    double *out_energy, uint32_t *out_where, int *out_mat, uint32_t *out_id)
+{
+    __shared__ unsigned int s_cnt[kNumMaterials], s_base[kNumMaterials];
+    if (threadIdx.x < kNumMaterials) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long base = (long)blockIdx.x * (256 * kPartItems);
+    int grp[kPartItems];
+    unsigned int rank[kPartItems];
+#pragma unroll
+    for (int i = 0; i < kPartItems; i++) {
+        const long t = base + i * 256 + threadIdx.x;
+        grp[i] = -1;
+        if (t < count) {
+            const int m = mat[t];
+            grp[i] = fuel_or_not ? (m != 0) : m;
+            rank[i] = atomicAdd(&s_cnt[grp[i]], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumMaterials && s_cnt[threadIdx.x]) {
+        // start of this group = sizes of the groups before it
+        unsigned int start = 0;
+        if (fuel_or_not) { if (threadIdx.x == 1) start = mat_histogram[0]; }
+        else for (int m = 0; m < (int)threadIdx.x; m++) start += mat_histogram[m];
+        s_base[threadIdx.x] = start + atomicAdd(cursor + threadIdx.x, s_cnt[threadIdx.x]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPartItems; i++) {
+        const long t = base + i * 256 + threadIdx.x;
+        if (grp[i] >= 0) {
+            const unsigned int pos = s_base[grp[i]] + rank[i];
+            out_energy[pos] = energy[t];
+            out_where[pos] = where[t];
+            if (out_mat) out_mat[pos] = mat[t];
+            out_id[pos] = (uint32_t)t;
+        }
+    }
+}
+
+// Apply a permutation (from the radix sort, -k 6): grouped copies of energy / where.
+__global__ void __launch_bounds__(256)
+xs_gather_kernel(const uint32_t *perm, const double *energy, const uint32_t *where, long count,
+                 double *out_energy, uint32_t *out_where)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const uint32_t at = perm[t];
+        out_energy[t] = energy[at];
+        out_where[t] = where[at];
+    }
 }
 
 // ---------------------------------------------------------------------------------------

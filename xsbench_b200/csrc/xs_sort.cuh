@@ -25,9 +25,11 @@ constexpr int kSortWarps = kSortThreads / 32;
 
 struct SortScratch {
     unsigned int *tile_hist = nullptr;      // [kRadix][n_tiles]
+    unsigned int *chunk_sum = nullptr;      // scan partials
     long n_tiles_capacity = 0;
 };
 
+// (the struct must be declared before the helpers below)
 inline int sort_scratch_alloc(SortScratch &s, long capacity_keys)
 {
     const long tiles = (capacity_keys + kSortTile - 1) / kSortTile;
@@ -35,10 +37,18 @@ inline int sort_scratch_alloc(SortScratch &s, long capacity_keys)
     cudaFree(s.tile_hist);
     s.tile_hist = nullptr;
     if (cudaMalloc(&s.tile_hist, (size_t)tiles * kRadix * sizeof(unsigned int)) != cudaSuccess) return -1;
+    cudaFree(s.chunk_sum);
+    s.chunk_sum = nullptr;
+    const long chunks = (tiles * kRadix + 4095) / 4096;
+    if (cudaMalloc(&s.chunk_sum, (size_t)chunks * sizeof(unsigned int)) != cudaSuccess) return -1;
     s.n_tiles_capacity = tiles;
     return 0;
 }
-inline void sort_scratch_free(SortScratch &s) { cudaFree(s.tile_hist); s.tile_hist = nullptr; s.n_tiles_capacity = 0; }
+inline void sort_scratch_free(SortScratch &s)
+{
+    cudaFree(s.tile_hist); cudaFree(s.chunk_sum);
+    s.tile_hist = nullptr; s.chunk_sum = nullptr; s.n_tiles_capacity = 0;
+}
 
 XS_DEV uint32_t sort_digit(uint32_t key, int shift, uint32_t mask, int nonzero_flag)
 {
@@ -63,19 +73,15 @@ sort_hist_kernel(const uint32_t *__restrict__ keys, long n, int shift, uint32_t 
     tile_hist[(long)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// In-place exclusive scan of `total` counters by one block of 1024 threads.
-__global__ void __launch_bounds__(1024)
-sort_scan_kernel(unsigned int *data, long total)
+// In-place exclusive scan of `total` counters in two launches: per-chunk sums, then each block
+// adds the sums of the chunks before it and scans its own chunk (4096 counters per block).
+constexpr int kScanThreads = 1024;
+constexpr int kScanChunk = kScanThreads * 4;
+
+XS_DEV unsigned int block_exclusive_scan(unsigned int v, unsigned int *warp_sums, unsigned int *total)
 {
-    __shared__ unsigned int warp_sums[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long chunk = (total + 1023) / 1024;
-    const long lo = (long)tid * chunk < total ? (long)tid * chunk : total;
-    const long hi = lo + chunk < total ? lo + chunk : total;
-    unsigned int sum = 0;
-    for (long i = lo; i < hi; i++) sum += data[i];
-    // block exclusive scan of the per-thread sums
-    unsigned int incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int incl = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const unsigned int t = __shfl_up_sync(kFullMask, incl, off);
@@ -84,17 +90,51 @@ sort_scan_kernel(unsigned int *data, long total)
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        unsigned int w = warp_sums[lane], wi = w;
+        const unsigned int w = warp_sums[lane];
+        unsigned int wi = w;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const unsigned int t = __shfl_up_sync(kFullMask, wi, off);
             if (lane >= off) wi += t;
         }
         warp_sums[lane] = wi - w;
+        if (lane == 31 && total) *total = wi;
     }
     __syncthreads();
-    unsigned int run = warp_sums[warp] + incl - sum;
-    for (long i = lo; i < hi; i++) { const unsigned int v = data[i]; data[i] = run; run += v; }
+    const unsigned int r = warp_sums[warp] + incl - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+sort_chunk_sum_kernel(const unsigned int *data, long total, unsigned int *chunk_sum)
+{
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int block_total;
+    const long base = (long)blockIdx.x * kScanChunk + threadIdx.x * 4;
+    unsigned int v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (base + i < total) v += data[base + i];
+    block_exclusive_scan(v, warp_sums, &block_total);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = block_total;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+sort_scan_kernel(unsigned int *data, long total, const unsigned int *chunk_sum)
+{
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int prefix;
+    // sum of all chunks before this one
+    unsigned int before = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += kScanThreads) before += chunk_sum[c];
+    block_exclusive_scan(before, warp_sums, &prefix);      // prefix (shared) <- block total
+    const long base = (long)blockIdx.x * kScanChunk + threadIdx.x * 4;
+    unsigned int v[4], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[i] = base + i < total ? data[base + i] : 0u; sum += v[i]; }
+    unsigned int run = prefix + block_exclusive_scan(sum, warp_sums, nullptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (base + i < total) { data[base + i] = run; run += v[i]; }
 }
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -167,12 +207,15 @@ inline int sort_lookups(SortScratch &s, uint32_t *key[2], uint32_t *perm[2], lon
         const int bits = std::min(8, hi_bit - shift);
         const uint32_t mask = (1u << bits) - 1u;
         sort_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(key[cur], n, shift, mask, nonzero_flag, s.tile_hist, n_tiles);
-        sort_scan_kernel<<<1, 1024, 0, stream>>>(s.tile_hist, (long)n_tiles * kRadix);
+        const long n_counters = (long)n_tiles * kRadix;
+        const int n_chunks = (int)((n_counters + kScanChunk - 1) / kScanChunk);
+        sort_chunk_sum_kernel<<<n_chunks, kScanThreads, 0, stream>>>(s.tile_hist, n_counters, s.chunk_sum);
+        sort_scan_kernel<<<n_chunks, kScanThreads, 0, stream>>>(s.tile_hist, n_counters, s.chunk_sum);
         sort_scatter_kernel<<<n_tiles, kSortThreads, 0, stream>>>(key[cur], first ? nullptr : perm[cur], key[cur ^ 1],
                                                                   perm[cur ^ 1], n, shift, mask, nonzero_flag,
                                                                   s.tile_hist, n_tiles);
         if (cudaGetLastError() != cudaSuccess) return -1;
-        *launches += 3;
+        *launches += 4;
         cur ^= 1;
         first = false;
     }
