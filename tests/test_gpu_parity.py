@@ -112,6 +112,34 @@ def test_lookup_samples_matches_oracle(small):
     assert res.h2d_bytes == len(e) * 12 and res.d2h_bytes >= len(e) * 40
 
 
+def test_sweep_path_is_bit_identical_to_reference_order(small):
+    """xs_gpu_lookup_samples runs the grouped, windowed sweep (same kernels as -k 4/5/6).  It adds
+    the per-nuclide terms in the reference's order with the reference's roundings (division by
+    Newton-Markstein correction of a stored reciprocal = correctly rounded quotient), so the
+    vectors must equal the oracle's bit for bit, not just within 1e-12."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    e = rng.random(n); m = rng.integers(0, 12, n).astype(np.int32)
+    res, macro = small.gpu.lookup_samples(e, m, want_macro_xs=True)
+    v, omacro = small.oracle.lookup_samples(e, m)
+    assert res.verification == v and res.n_lookups == n
+    assert np.array_equal(macro, omacro)
+
+
+def test_division_is_exact(small):
+    """Stress the reciprocal-based division: energies ON grid points (f = 0 or 1), one ulp
+    around them, and at the ends of every nuclide's grid."""
+    g = small.oracle.nuclide_grid[0::6]
+    e = np.concatenate([g[::7], np.nextafter(g[::7], 0), np.nextafter(g[::7], 1)])
+    e = e[(e > 0) & (e < 1)]
+    rng = np.random.default_rng(9)
+    m = rng.integers(0, 12, len(e)).astype(np.int32)
+    res, macro = small.gpu.lookup_samples(e, m, want_macro_xs=True)
+    v, omacro = small.oracle.lookup_samples(e, m)
+    assert res.verification == v
+    assert np.array_equal(macro, omacro)
+
+
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1000])
 def test_lookup_samples_ragged_sizes(small, n):
     rng = np.random.default_rng(n)

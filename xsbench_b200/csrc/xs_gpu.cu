@@ -80,6 +80,7 @@ struct DeviceState {
     unsigned int *histogram = nullptr;     // device [16]
     unsigned long long *h_accum = nullptr; // pinned host [2]
     unsigned int *h_hist = nullptr;        // pinned host [16]
+    int h_mat_first[XS_NUM_MATERIALS + 1] = {};
     long sample_capacity = 0;
     double *samp_e = nullptr;
     int *samp_mat = nullptr;
@@ -204,7 +205,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     // pair records (B200 layout for the windowed sweep): one 128-byte line per (nuclide, k)
     const size_t pair_bytes = (size_t)n_points * 8 * sizeof(double2);
     CUDA_TRY(cudaMalloc(&d.pairs, pair_bytes));
-    xs::xs_build_pairs_kernel<<<d.sm_count * 16, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, d.pairs);
+    xs::xs_build_pairs_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, d.pairs);
     CUDA_TRY(cudaGetLastError());
     d.resident_bytes += pair_bytes;
     P.pairs = d.pairs;
@@ -257,6 +258,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
             nuc[first[m] + j] = sd->mats[(size_t)m * sd->max_num_nucs + j];
             conc[first[m] + j] = sd->concs[(size_t)m * sd->max_num_nucs + j];
         }
+    memcpy(d.h_mat_first, first, sizeof first);
     CUDA_TRY(cudaMalloc(&d.mat_first, sizeof first));
     CUDA_TRY(cudaMalloc(&d.mat_nuc, (size_t)total * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d.mat_conc, (size_t)total * sizeof(double)));
@@ -377,40 +379,67 @@ int launch_event(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs
     return XS_OK;
 }
 
-// Windowed nuclide sweep over the lookups of one material: slots [offset, offset+count) of the
-// grouped arrays (grp_e / grp_where / id); one launch per nuclide window, see xs_window_kernel.
-int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const uint32_t *id, long offset, long count, int mat,
-                 xs::BatchSink sink)
+// One launch of the window kernel over `n_seg` segments.
+int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, xs::BatchSink sink)
 {
-    if (count <= 0) return XS_OK;
-    const int n_nuclides = ctx->num_nucs[mat];
+    long groups = 0;
+    for (int i = 0; i < a.n_seg; i++) {
+        a.seg[i].group_begin = groups;
+        groups += (a.seg[i].count + xs::kSweepSlots - 1) / xs::kSweepSlots;
+    }
+    if (groups == 0) return XS_OK;
+    a.n_groups = groups;
+    a.energy = d.grp_e;
+    a.where = d.grp_where;
+    a.partial = d.sweep_partial;
     WindowKernel k = window_kernel(ctx->grid_type);
     int blocks = 0;
     int rc = persistent_grid(ctx, d, (const void *)k, &blocks, 0);
     if (rc != XS_OK) return rc;
-    const long groups = (count + xs::kSweepSlots - 1) / xs::kSweepSlots;
     const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
     if (blocks > max_useful) blocks = (int)max_useful;
-    const int passes = (n_nuclides + ctx->window - 1) / ctx->window;
-    const int width = (n_nuclides + passes - 1) / passes;          // balanced windows
-    for (int p = 0; p < passes; p++) {
-        xs::WindowArgs a{};
-        a.energy = d.grp_e;
-        a.where = d.grp_where;
-        a.sample_id = id;
-        a.partial = d.sweep_partial;
-        a.offset = offset;
-        a.count = count;
-        a.mat = mat;
-        a.j_begin = p * width;
-        a.j_end = std::min(n_nuclides, (p + 1) * width);
-        a.first_window = p == 0;
-        a.last_window = p == passes - 1;
-        k<<<blocks, xs::kBlockThreads, 0, d.stream>>>(d.P, a, sink);
-        CUDA_TRY(cudaGetLastError());
-        d.launches++;
-    }
+    k<<<blocks, xs::kBlockThreads, 0, d.stream>>>(d.P, a, sink);
+    CUDA_TRY(cudaGetLastError());
+    d.launches++;
     return XS_OK;
+}
+
+// Windowed nuclide sweep over lookups grouped by material (grp_e / grp_where / id):
+// `count[m]` lookups of material mats[m] starting at slot `offset[m]`.  Materials that need
+// several windows (fuel) get one launch per window; all single-window materials share one.
+int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const uint32_t *id, int n_mats, const int *mats,
+                 const long *offset, const long *count, xs::BatchSink sink)
+{
+    const int window = std::min(ctx->window, xs::kMaxWindow);
+    xs::WindowArgs small{};
+    small.sample_id = id;
+    small.first_window = small.last_window = 1;
+    int rc = XS_OK;
+    for (int i = 0; i < n_mats && rc == XS_OK; i++) {
+        const int m = mats[i], n = ctx->num_nucs[m];
+        if (count[i] <= 0) continue;
+        const int passes = (n + window - 1) / window;
+        const int width = (n + passes - 1) / passes;           // balanced windows
+        if (passes == 1) {
+            xs::WindowSegment &sgm = small.seg[small.n_seg++];
+            sgm.offset = offset[i]; sgm.count = count[i]; sgm.first = d.h_mat_first[m];
+            sgm.j_begin = 0; sgm.j_end = n;
+            continue;
+        }
+        for (int p = 0; p < passes && rc == XS_OK; p++) {
+            xs::WindowArgs a{};
+            a.sample_id = id;
+            a.n_seg = 1;
+            a.seg[0].offset = offset[i]; a.seg[0].count = count[i]; a.seg[0].first = d.h_mat_first[m];
+            a.seg[0].j_begin = p * width;
+            a.seg[0].j_end = std::min(n, (p + 1) * width);
+            a.first_window = p == 0;
+            a.last_window = p == passes - 1;
+            rc = launch_window(ctx, d, a, sink);
+        }
+    }
+    if (rc == XS_OK && small.n_seg) rc = launch_window(ctx, d, small, sink);
+    return rc;
 }
 
 int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bool with_where, bool with_key,
@@ -456,10 +485,11 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
     // group sizes: the sampler's histogram (device -> pinned host; the launches below need them)
     CUDA_TRY(cudaMemcpyAsync(d.h_hist, d.histogram, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
-    long offset = 0;
     if (kernel_id == 5) {
         const long n_fuel = d.h_hist[0];
-        rc = launch_sweep(ctx, d, id, 0, n_fuel, 0, sink);
+        const int fuel = 0;
+        const long zero = 0;
+        rc = launch_sweep(ctx, d, id, 1, &fuel, &zero, &n_fuel, sink);
         if (rc == XS_OK && count > n_fuel) {
             xs::BatchSource rest{};
             rest.energy = d.grp_e + n_fuel;
@@ -470,11 +500,13 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
         }
         return rc;
     }
-    for (int m = 0; m < XS_NUM_MATERIALS && rc == XS_OK; m++) {
-        rc = launch_sweep(ctx, d, id, offset, d.h_hist[m], m, sink);
+    int mats[XS_NUM_MATERIALS];
+    long offs[XS_NUM_MATERIALS], cnts[XS_NUM_MATERIALS], offset = 0;
+    for (int m = 0; m < XS_NUM_MATERIALS; m++) {
+        mats[m] = m; offs[m] = offset; cnts[m] = d.h_hist[m];
         offset += d.h_hist[m];
     }
-    return rc;
+    return launch_sweep(ctx, d, id, XS_NUM_MATERIALS, mats, offs, cnts, sink);
 }
 
 // One device's share of an event-mode run: ids [first_id, first_id + count).
@@ -731,7 +763,7 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
     for (int g = 0; g < ng; g++) {
         DeviceState &d = ctx->dev[g];
         const long lo = n * g / ng, cnt = n * (g + 1) / ng - lo;
-        int rc = ensure_sample_buffers(d, cnt, false);
+        int rc = ensure_sample_buffers(d, cnt, ctx->sweep != 0);
         if (rc == XS_OK && h_macro_xs_out) rc = ensure_dump_buffer(d, cnt);
         if (rc != XS_OK) return rc;
         CUDA_TRY(cudaSetDevice(d.device));
@@ -741,15 +773,27 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         CUDA_TRY(cudaMemcpyAsync(d.samp_mat, h_mat + lo, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
         CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
         CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
-        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
-        CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
-        xs::BatchSource src{};
-        src.energy = d.samp_e; src.mat = d.samp_mat; src.count = cnt;
-        src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
+        CUDA_TRY(cudaMemsetAsync(d.histogram, 0, 16 * sizeof(unsigned int), d.stream));
         xs::BatchSink sink{};
         sink.accum = d.accum;
         sink.macro_out = h_macro_xs_out ? d.dump_macro : nullptr;
-        rc = launch_event(ctx, d, src, sink, 0);
+        if (ctx->sweep && cnt > 0) {
+            // group by material, then the windowed nuclide sweep (same pipeline as -k 4)
+            const int blocks = (int)std::min<long>((cnt + 255) / 256, (long)d.sm_count * 16);
+            xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, cnt, d.samp_e, d.samp_mat,
+                                                             d.samp_where, d.histogram);
+            CUDA_TRY(cudaGetLastError());
+            d.launches++;
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+            rc = enqueue_grouped_lookup(ctx, d, 4, cnt, sink);
+        } else {
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+            xs::BatchSource src{};
+            src.energy = d.samp_e; src.mat = d.samp_mat; src.count = cnt;
+            src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
+            rc = launch_event(ctx, d, src, sink, 0);
+        }
         if (rc != XS_OK) return rc;
         if (h_macro_xs_out)
             CUDA_TRY(cudaMemcpyAsync(h_macro_xs_out + 5 * lo, d.dump_macro, (size_t)cnt * 5 * sizeof(double), cudaMemcpyDeviceToHost, d.stream));

@@ -361,8 +361,8 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 }
 
 // ---------------------------------------------------------------------------------------
-// Window kernel: lookups of ONE material, restricted to the nuclide window [j_begin, j_end)
-// of that material's nuclide list ("windowed nuclide sweep").
+// Window kernel: lookups grouped by material, restricted to one nuclide window [j_begin, j_end)
+// of the material's nuclide list ("windowed nuclide sweep").
 //
 // Why: the gather is 96 B per (lookup, nuclide) at a random grid point of that nuclide.  If
 // every warp works on its own lookup front to back, the whole grid is the working set and
@@ -372,125 +372,175 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 // nuclides than one window (fuel: 321) takes several launches; the five partial sums of a
 // lookup travel between launches through a 48-byte record in global memory (2 x 113 MB per
 // pass for fuel -- noise next to the gather).  Stream order is the only synchronisation.
+// Materials that fit one window (all but fuel) share ONE launch: a launch works on up to 12
+// segments (material, slot range, window).
 //
-// Layout: the gather reads PAIR RECORDS built once at init (xs_build_pairs_kernel): for each
-// (nuclide, k) one 128-byte-aligned record [lo.c0 hi.c0 | lo.c1 hi.c1 | lo.c2 hi.c2 | pad]
-// with c0 = (energy,total) c1 = (elastic,absorbtion) c2 = (fission,nu_fission) of grid points
-// k and k+1.  The gather of one (lookup, nuclide) is then ONE 128-byte line.
+// Layout: the gather reads PAIR RECORDS built once at init (xs_build_pairs_kernel), one
+// 128-byte line per (nuclide, k), holding for grid points lo = k and hi = k+1:
+//     quarter 0: hi.total, hi.total-lo.total, hi.elastic, hi.elastic-lo.elastic
+//     quarter 1: hi.absorbtion, d(absorbtion), hi.fission, d(fission)
+//     quarter 2: hi.nu_fission, d(nu_fission), 0, 0
+//     quarter 3: hi.energy, d = hi.energy-lo.energy, 1/d, 0
+// The differences are the reference's own intermediate values (hi - lo rounded once), so
+// xs = hi - f*(hi-lo) is computed with the reference's roundings.
 //
-// Mapping ("transposed triple"): a warp owns 10 lookups (slots); lane c of a slot loads the
-// 32-byte third c of the slot's record with one 256-bit load -- 96 contiguous bytes per slot,
-// one L1 wavefront per slot and step (the reference-layout alternative costs 2 x 1.3).  Each
-// lane keeps the two channel sums of its chunk, accumulated in reference order j = 0,1,2,...
-// with the reference's operations, so macro_xs is bit-identical to the reference.  The record
-// numbers of the next 32 nuclides are resolved by the whole warp (coalesced index-row
-// segments) and staged in shared memory, so every index sector is requested once.
+// Mapping: a warp owns 8 lookups (slots) x 4 lanes; lane q of a slot loads quarter q of the
+// slot's record with ONE 256-bit load: 128 contiguous bytes per slot, one L1 wavefront per
+// (lookup, nuclide).  Lane 3 derives the interpolation factor f = (hi.E - E)/d from the stored
+// reciprocal with one Newton-Markstein correction (q = n*inv; r = fma(-d,q,n); f = fma(r,inv,q)
+// -- the correctly rounded quotient, see tests/test_gpu_parity.py::test_division_is_exact) and
+// broadcasts it; lanes 0..2 accumulate two channels each in reference order j = 0,1,2,....
+// The record numbers of a whole window are resolved up front by all 32 lanes (coalesced
+// index-row segments) and staged in shared memory; the gather loop is software-pipelined
+// (2 x kSweepUnroll loads in flight per lane) and free of predication (padded steps carry
+// concentration 0).
 // ---------------------------------------------------------------------------------------
 #ifndef XS_SWEEP_UNROLL
-#define XS_SWEEP_UNROLL 4
+#define XS_SWEEP_UNROLL 2
 #endif
 #ifndef XS_SWEEP_BLOCKS
 #define XS_SWEEP_BLOCKS 4
 #endif
 constexpr int kSweepUnroll = XS_SWEEP_UNROLL;
-constexpr int kSweepSlots = 10;
+constexpr int kSweepSlots = 8;
+constexpr int kMaxWindow = 64;             // nuclides per window (staging capacity)
+constexpr int kMaxSegments = 12;
+
+struct WindowSegment {
+    long offset;               // first slot of this material in the grouped arrays
+    long count;                // lookups of this material
+    long group_begin;          // first warp-group of this segment inside the launch
+    int  first;                // mat_first[material]
+    int  j_begin, j_end;       // nuclide window inside the material's list
+    int  pad;
+};
 
 struct WindowArgs {
-    const double   *energy;    // [.. offset+count) energies grouped by material
+    const double   *energy;    // energies grouped by material
     const uint32_t *where;     // same order: UEG row / hash bin
     const uint32_t *sample_id; // same order: original sample index (only for macro_xs dumps)
-    double2        *partial;   // [3 * slots] partial sums between windows (chunk c at 3*slot + c)
-    long  offset;              // first slot of this material
-    long  count;               // lookups of this material
-    int   mat;
-    int   j_begin, j_end;      // nuclide window inside the material's list
+    double2        *partial;   // [3 * slots] partial sums between windows
+    long  n_groups;            // warp-groups in this launch
+    int   n_seg;
     int   first_window, last_window;
+    WindowSegment seg[kMaxSegments];
 };
+
+struct Quarter { double a, da, b, db; };
+
+XS_DEV Quarter ldg_quarter(const double2 *p)
+{
+    Quarter v;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v.a), "=d"(v.da), "=d"(v.b), "=d"(v.db) : "l"(p));
+    return v;
+}
+
+// One step: lane 3 turns (hi.E, d, 1/d) into f and broadcasts it; every lane folds its two
+// channels.  conc == 0 for padded steps.
+XS_DEV void sweep_step(const Quarter &v, double e, double conc, int f_src, double &acc_x, double &acc_y)
+{
+    const double n = v.a - e;                          // hi.E - E          (lane 3)
+    const double q = n * v.b;                          // n * (1/d)
+    const double r = __fma_rn(-v.da, q, n);            // n - d*q, exact
+    const double f_own = __fma_rn(r, v.b, q);          // correctly rounded n/d
+    const double f = __shfl_sync(kFullMask, f_own, f_src);
+    acc_x += (v.a - f * v.da) * conc;
+    acc_y += (v.b - f * v.db) * conc;
+}
 
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_SWEEP_BLOCKS)
 xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 {
     __shared__ unsigned long long s_part[kWarpsPerBlock];
-    __shared__ uint32_t s_rec[kWarpsPerBlock][kSweepSlots][33];
-    __shared__ int s_first;
-    if (threadIdx.x == 0) s_first = P.mat_first[A.mat];
-    __syncthreads();
+    __shared__ uint32_t s_rec[kWarpsPerBlock][kSweepSlots][kMaxWindow + 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = lane / 3, chunk = lane - 3 * slot;
-    const bool lane_on = lane < 3 * kSweepSlots;
-    const int f_src = lane - chunk;
-    const int first = s_first;
-    const long n_groups = (A.count + kSweepSlots - 1) / kSweepSlots;
+    const int slot = lane >> 2, quarter = lane & 3;
+    const int f_src = lane | 3;
+    const double2 *my_pairs = P.pairs + 2 * quarter;
     const long warp_global = (long)blockIdx.x * kWarpsPerBlock + warp;
     const long warp_stride = (long)gridDim.x * kWarpsPerBlock;
     unsigned long long my_sum = 0, my_count = 0;
 
-    for (long g = warp_global; g < n_groups; g += warp_stride) {
-        const long t = A.offset + g * kSweepSlots + slot;    // global slot
-        const bool on = lane_on && g * kSweepSlots + slot < A.count;
+    for (long g = warp_global; g < A.n_groups; g += warp_stride) {
+        int sg = 0;                                          // warp-uniform segment lookup
+        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;
+        const WindowSegment &S = A.seg[sg];
+        const long in_seg = (g - S.group_begin) * kSweepSlots + slot;
+        const long t = S.offset + in_seg;                    // global slot
+        const bool on = in_seg < S.count;
+        const int jn = S.j_end - S.j_begin;
+        const int n_steps = (jn + 2 * kSweepUnroll - 1) / (2 * kSweepUnroll) * (2 * kSweepUnroll);
+
         double e = 0.5;
         long where = 0;
         double acc_x = 0.0, acc_y = 0.0;
         if (on) {
             e = A.energy[t];
             where = A.where[t];
-            if (!A.first_window) {
-                const double2 part = A.partial[3 * t + chunk];
+            if (!A.first_window && quarter < 3) {
+                const double2 part = A.partial[3 * t + quarter];
                 acc_x = part.x;
                 acc_y = part.y;
             }
         }
 
-        for (int jb = A.j_begin; jb < A.j_end; jb += 32) {
-            const int jn = min(32, A.j_end - jb);
-            // resolve the record numbers of nuclides [jb, jb+jn) for the 10 lookups of this warp
-            __syncwarp();
-            const int my_nuc = lane < jn ? P.mat_nuc[first + jb + lane] : 0;
+        // ---- resolve the record numbers of the window for the 8 lookups of this warp ------
+        __syncwarp();
+        for (int jb = 0; jb < n_steps; jb += 32) {
+            const int j = jb + lane;
+            const int my_nuc = j < jn ? P.mat_nuc[S.first + S.j_begin + j] : 0;
 #pragma unroll
             for (int s = 0; s < kSweepSlots; s++) {
-                const long w_s = __shfl_sync(kFullMask, where, 3 * s);
-                const double e_s = __shfl_sync(kFullMask, e, 3 * s);
-                const bool slot_on = __shfl_sync(kFullMask, (int)on, 3 * s);
-                if (slot_on && lane < jn)
-                    s_rec[warp][s][lane] = (uint32_t)((long)my_nuc * P.n_gp + nuclide_low<GRID>(P, e_s, w_s, my_nuc));
+                const long w_s = __shfl_sync(kFullMask, where, 4 * s);
+                const double e_s = __shfl_sync(kFullMask, e, 4 * s);
+                const bool slot_on = __shfl_sync(kFullMask, (int)on, 4 * s);
+                if (j < n_steps) {
+                    uint32_t rec = 0;                        // padded steps / idle slots: record 0
+                    if (slot_on && j < jn)
+                        rec = (uint32_t)((long)my_nuc * P.n_gp + nuclide_low<GRID>(P, e_s, w_s, my_nuc));
+                    s_rec[warp][s][j] = rec;
+                }
             }
-            __syncwarp();
+        }
+        __syncwarp();
 
-            for (int j0 = 0; j0 < jn; j0 += kSweepUnroll) {
-                double2 lo[kSweepUnroll], hi[kSweepUnroll];
+        // ---- software-pipelined gather -------------------------------------------------------
+        const uint32_t *my_rec = s_rec[warp][slot];
+        const int c0 = S.first + S.j_begin;
+        Quarter A0[kSweepUnroll], A1[kSweepUnroll];
 #pragma unroll
-                for (int u = 0; u < kSweepUnroll; u++) {
-                    lo[u] = make_double2(0.0, 0.0);
-                    hi[u] = make_double2(1.0, 0.0);
-                    if (on && j0 + u < jn)
-                        ldg_pair(P.pairs + 8 * (long)s_rec[warp][slot][j0 + u] + 2 * chunk, lo[u], hi[u]);
-                }
+        for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
+        for (int j0 = 0; j0 < n_steps; j0 += 2 * kSweepUnroll) {
 #pragma unroll
-                for (int u = 0; u < kSweepUnroll; u++) {
-                    const double f_own = (hi[u].x - e) / (hi[u].x - lo[u].x);       // used from chunk 0
-                    const double f = __shfl_sync(kFullMask, f_own, f_src);
-                    if (j0 + u < jn) {                                              // warp-uniform
-                        const double conc = c_mat_conc[first + jb + j0 + u];
-                        if (on) {
-                            acc_x += lerp_xs(lo[u].x, hi[u].x, f) * conc;
-                            acc_y += lerp_xs(lo[u].y, hi[u].y, f) * conc;
-                        }
-                    }
-                }
+            for (int u = 0; u < kSweepUnroll; u++) A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++) {
+                const int j = j0 + u;
+                sweep_step(A0[u], e, j < jn ? c_mat_conc[c0 + j] : 0.0, f_src, acc_x, acc_y);
+            }
+            if (j0 + 2 * kSweepUnroll < n_steps) {
+#pragma unroll
+                for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++) {
+                const int j = j0 + kSweepUnroll + u;
+                sweep_step(A1[u], e, j < jn ? c_mat_conc[c0 + j] : 0.0, f_src, acc_x, acc_y);
             }
         }
 
         if (!A.last_window) {
-            if (on) A.partial[3 * t + chunk] = make_double2(acc_x, acc_y);
+            if (on && quarter < 3) A.partial[3 * t + quarter] = make_double2(acc_x, acc_y);
             continue;                                        // warp-uniform
         }
-        // chunk0 = (energy, total) chunk1 = (elastic, absorbtion) chunk2 = (fission, nu_fission)
-        const double c1x = __shfl_down_sync(kFullMask, acc_x, 1), c1y = __shfl_down_sync(kFullMask, acc_y, 1);
-        const double c2x = __shfl_down_sync(kFullMask, acc_x, 2), c2y = __shfl_down_sync(kFullMask, acc_y, 2);
-        if (on && chunk == 0) {
-            const double v[5] = {acc_y, c1x, c1y, c2x, c2y};
+        // lane 0 = (total, elastic)  lane 1 = (absorbtion, fission)  lane 2 = (nu_fission, -)
+        const double q1x = __shfl_down_sync(kFullMask, acc_x, 1), q1y = __shfl_down_sync(kFullMask, acc_y, 1);
+        const double q2x = __shfl_down_sync(kFullMask, acc_x, 2);
+        if (on && quarter == 0) {
+            const double v[5] = {acc_x, acc_y, q1x, q1y, q2x};
             double gap;
             const int am = argmax5(v, gap);
             my_sum += (unsigned long long)(am + 1);
@@ -510,19 +560,29 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     }
 }
 
-// Pair records for the window kernel (init only).  Record r = nuc*n_gp + k (k <= n_gp-2):
-//   [0]=lo.c0 [1]=hi.c0 [2]=lo.c1 [3]=hi.c1 [4]=lo.c2 [5]=hi.c2 [6],[7]=padding
+// Pair records for the window kernel (init only); record r = nuc*n_gp + k, k <= n_gp-2.
 __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp, double2 *pairs)
 {
-    const long total = n_iso * n_gp * 8;
+    const long total = n_iso * n_gp;
     const long stride = (long)gridDim.x * blockDim.x;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long r = i >> 3;
-        const int q = (int)(i & 7);
-        const long k = r % n_gp;
-        double2 v = make_double2(0.0, 0.0);
-        if (q < 6 && k + 1 < n_gp) v = grid[3 * (r + (q & 1)) + (q >> 1)];
-        pairs[i] = v;
+    for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += stride) {
+        double2 out[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = make_double2(0.0, 0.0);
+        if (r % n_gp + 1 < n_gp) {
+            const double2 l0 = grid[3 * r], l1 = grid[3 * r + 1], l2 = grid[3 * r + 2];
+            const double2 h0 = grid[3 * r + 3], h1 = grid[3 * r + 4], h2 = grid[3 * r + 5];
+            const double d = h0.x - l0.x;
+            out[0] = make_double2(h0.y, h0.y - l0.y);        // total
+            out[1] = make_double2(h1.x, h1.x - l1.x);        // elastic
+            out[2] = make_double2(h1.y, h1.y - l1.y);        // absorbtion
+            out[3] = make_double2(h2.x, h2.x - l2.x);        // fission
+            out[4] = make_double2(h2.y, h2.y - l2.y);        // nu_fission
+            out[6] = make_double2(h0.x, d);                  // hi.E, d
+            out[7] = make_double2(1.0 / d, 0.0);             // correctly rounded reciprocal
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) pairs[8 * r + i] = out[i];
     }
 }
 
