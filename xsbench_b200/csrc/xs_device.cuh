@@ -51,8 +51,10 @@ struct Problem {
 };
 
 __constant__ double c_mat_threshold[kNumMaterials];
-constexpr int kMaxConstConc = 1024;
-__constant__ double c_mat_conc[kMaxConstConc];      // copy of Problem::mat_conc (uniform-datapath reads)
+// Concentrations for the window kernel: one zero-padded row per material, read through the
+// uniform datapath (LDC) with no bounds logic -- padded steps simply multiply by 0.
+constexpr int kConcStride = 512;
+__constant__ double c_conc_pad[kNumMaterials * kConcStride];
 
 // ---------------------------------------------------------------------------------------
 // LCG: x <- (a x + 1) mod 2^63
@@ -149,7 +151,7 @@ XS_DEV double ldg_grid_energy(const double2 *p)
 XS_DEV uint64_t policy_stream()
 {
     uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));   // pure: may be hoisted/CSE'd
     return p;
 }
 XS_DEV int ldg_index_stream(const int *p)         // unionized index row: touched once

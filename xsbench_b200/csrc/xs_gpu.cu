@@ -110,7 +110,7 @@ struct xs_gpu_ctx {
     int gather = xs::kTriple;
     int blocks_per_sm = 0;                 // 0 = from occupancy
     int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
-    int window = 40;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
+    int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
     size_t smem_bytes = 0;
@@ -281,9 +281,13 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         thr[i] = acc;
     }
     CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_mat_threshold, thr, sizeof thr, 0, cudaMemcpyHostToDevice, d.stream));
-    if (total > xs::kMaxConstConc)
-        return set_error(XS_ERR_UNSUPP, "material table has %d entries, more than the %d this build supports", total, xs::kMaxConstConc);
-    CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_mat_conc, conc.data(), (size_t)total * sizeof(double), 0, cudaMemcpyHostToDevice, d.stream));
+    if (sd->max_num_nucs + 16 > xs::kConcStride)
+        return set_error(XS_ERR_UNSUPP, "a material has %d nuclides, more than the %d this build supports", sd->max_num_nucs, xs::kConcStride - 16);
+    std::vector<double> conc_pad((size_t)XS_NUM_MATERIALS * xs::kConcStride, 0.0);
+    for (int m = 0; m < XS_NUM_MATERIALS; m++)
+        for (int j = 0; j < sd->num_nucs[m]; j++)
+            conc_pad[(size_t)m * xs::kConcStride + j] = sd->concs[(size_t)m * sd->max_num_nucs + j];
+    CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_conc_pad, conc_pad.data(), conc_pad.size() * sizeof(double), 0, cudaMemcpyHostToDevice, d.stream));
 
     // run scratch
     CUDA_TRY(cudaMalloc(&d.accum, 2 * sizeof(unsigned long long)));
@@ -394,11 +398,12 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, xs::BatchS
     a.partial = d.sweep_partial;
     WindowKernel k = window_kernel(ctx->grid_type);
     int blocks = 0;
-    int rc = persistent_grid(ctx, d, (const void *)k, &blocks, 0);
+    const size_t smem = (size_t)d.P.mat_total * sizeof(int);
+    int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
     if (rc != XS_OK) return rc;
     const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
     if (blocks > max_useful) blocks = (int)max_useful;
-    k<<<blocks, xs::kBlockThreads, 0, d.stream>>>(d.P, a, sink);
+    k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink);
     CUDA_TRY(cudaGetLastError());
     d.launches++;
     return XS_OK;
@@ -418,12 +423,16 @@ int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const uint32_t *id, int n_mats
     for (int i = 0; i < n_mats && rc == XS_OK; i++) {
         const int m = mats[i], n = ctx->num_nucs[m];
         if (count[i] <= 0) continue;
-        const int passes = (n + window - 1) / window;
-        const int width = (n + passes - 1) / passes;           // balanced windows
+        // windows of `window` nuclides (a multiple of the gather loop's step quantum); a short
+        // remainder is folded into the last window instead of costing a launch of its own
+        const int quantum = 2 * xs::kSweepUnroll;
+        const int width = std::max(quantum, std::min(window, xs::kMaxWindow - 8) / quantum * quantum);
+        int passes = (n + width - 1) / width;
+        if (passes > 1 && n - (passes - 1) * width <= 8) passes--;
         if (passes == 1) {
             xs::WindowSegment &sgm = small.seg[small.n_seg++];
             sgm.offset = offset[i]; sgm.count = count[i]; sgm.first = d.h_mat_first[m];
-            sgm.j_begin = 0; sgm.j_end = n;
+            sgm.j_begin = 0; sgm.j_end = n; sgm.mat = m;
             continue;
         }
         for (int p = 0; p < passes && rc == XS_OK; p++) {
@@ -431,8 +440,9 @@ int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const uint32_t *id, int n_mats
             a.sample_id = id;
             a.n_seg = 1;
             a.seg[0].offset = offset[i]; a.seg[0].count = count[i]; a.seg[0].first = d.h_mat_first[m];
+            a.seg[0].mat = m;
             a.seg[0].j_begin = p * width;
-            a.seg[0].j_end = std::min(n, (p + 1) * width);
+            a.seg[0].j_end = (p == passes - 1) ? n : (p + 1) * width;
             a.first_window = p == 0;
             a.last_window = p == passes - 1;
             rc = launch_window(ctx, d, a, sink);
@@ -680,7 +690,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->gather = env_int("XSB200_GATHER", xs::kTriple) ? xs::kTriple : xs::kLanePerNuclide;
     ctx->blocks_per_sm = env_int("XSB200_BLOCKS_PER_SM", 0);
     ctx->sweep = env_int("XSB200_SWEEP", 1);
-    ctx->window = std::max(1, env_int("XSB200_WINDOW", 40));
+    ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);

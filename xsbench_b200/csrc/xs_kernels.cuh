@@ -412,7 +412,7 @@ struct WindowSegment {
     long group_begin;          // first warp-group of this segment inside the launch
     int  first;                // mat_first[material]
     int  j_begin, j_end;       // nuclide window inside the material's list
-    int  pad;
+    int  mat;
 };
 
 struct WindowArgs {
@@ -455,6 +455,9 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 {
     __shared__ unsigned long long s_part[kWarpsPerBlock];
     __shared__ uint32_t s_rec[kWarpsPerBlock][kSweepSlots][kMaxWindow + 1];
+    extern __shared__ int s_nuc[];                           // [mat_total] nuclide ids of all materials
+    for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
+    __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = lane >> 2, quarter = lane & 3;
@@ -462,7 +465,23 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     const double2 *my_pairs = P.pairs + 2 * quarter;
     const long warp_global = (long)blockIdx.x * kWarpsPerBlock + warp;
     const long warp_stride = (long)gridDim.x * kWarpsPerBlock;
-    unsigned long long my_sum = 0, my_count = 0;
+    unsigned int my_sum = 0, my_count = 0;                   // per thread: far below 2^32
+
+    // energy / row of the group after this one are requested one iteration ahead
+    double e_next = 0.5;
+    uint32_t where_next = 0;
+    {
+        const long g0 = warp_global;
+        if (g0 < A.n_groups) {
+            int sg = 0;
+            while (sg + 1 < A.n_seg && g0 >= A.seg[sg + 1].group_begin) sg++;
+            const long in_seg = (g0 - A.seg[sg].group_begin) * kSweepSlots + slot;
+            if (in_seg < A.seg[sg].count) {
+                e_next = A.energy[A.seg[sg].offset + in_seg];
+                where_next = A.where[A.seg[sg].offset + in_seg];
+            }
+        }
+    }
 
     for (long g = warp_global; g < A.n_groups; g += warp_stride) {
         int sg = 0;                                          // warp-uniform segment lookup
@@ -474,62 +493,103 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         const int jn = S.j_end - S.j_begin;
         const int n_steps = (jn + 2 * kSweepUnroll - 1) / (2 * kSweepUnroll) * (2 * kSweepUnroll);
 
-        double e = 0.5;
-        long where = 0;
+        const double e = e_next;
+        const long where = where_next;
         double acc_x = 0.0, acc_y = 0.0;
-        if (on) {
-            e = A.energy[t];
-            where = A.where[t];
-            if (!A.first_window && quarter < 3) {
-                const double2 part = A.partial[3 * t + quarter];
-                acc_x = part.x;
-                acc_y = part.y;
+        if (on && !A.first_window && quarter < 3) {
+            const double2 part = A.partial[3 * t + quarter];
+            acc_x = part.x;
+            acc_y = part.y;
+        }
+        {   // prefetch the next group's sample
+            const long gn = g + warp_stride;
+            e_next = 0.5;
+            where_next = 0;
+            if (gn < A.n_groups) {
+                int sn = sg;
+                while (sn + 1 < A.n_seg && gn >= A.seg[sn + 1].group_begin) sn++;
+                const long in_n = (gn - A.seg[sn].group_begin) * kSweepSlots + slot;
+                if (in_n < A.seg[sn].count) {
+                    e_next = A.energy[A.seg[sn].offset + in_n];
+                    where_next = A.where[A.seg[sn].offset + in_n];
+                }
             }
         }
 
         // ---- resolve the record numbers of the window for the 8 lookups of this warp ------
+        // The 8 x n_steps (slot, step) pairs are spread over the 32 lanes, `row_len` (a power
+        // of two >= n_steps) pairs per slot, so a 4-nuclide material needs one round, a
+        // 32-nuclide window eight.  Steps [jn, n_steps) are padding: record 0, concentration 0.
         __syncwarp();
-        for (int jb = 0; jb < n_steps; jb += 32) {
-            const int j = jb + lane;
-            const int my_nuc = j < jn ? P.mat_nuc[S.first + S.j_begin + j] : 0;
-#pragma unroll
-            for (int s = 0; s < kSweepSlots; s++) {
-                const long w_s = __shfl_sync(kFullMask, where, 4 * s);
-                const double e_s = __shfl_sync(kFullMask, e, 4 * s);
-                const bool slot_on = __shfl_sync(kFullMask, (int)on, 4 * s);
-                if (j < n_steps) {
-                    uint32_t rec = 0;                        // padded steps / idle slots: record 0
-                    if (slot_on && j < jn)
-                        rec = (uint32_t)((long)my_nuc * P.n_gp + nuclide_low<GRID>(P, e_s, w_s, my_nuc));
-                    s_rec[warp][s][j] = rec;
+        {
+            const int row_shift = 32 - __clz(n_steps - 1);           // log2(row_len), n_steps >= 4
+            const int slots_on = (int)min((long)kSweepSlots, S.count - (g - S.group_begin) * kSweepSlots);
+            const uint32_t where32 = (uint32_t)where;
+            const int *nucs = s_nuc + S.first + S.j_begin;
+            if (row_shift <= 5) {
+                // a lane keeps its step j in every round; rounds walk over the slots
+                const int j = lane & ((1 << row_shift) - 1);
+                const int nuc = j < jn ? nucs[j] : 0;
+                const int per_round = 32 >> row_shift;
+                for (int s = lane >> row_shift; s < kSweepSlots; s += per_round) {
+                    const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * s);
+                    double e_s = 0.0;
+                    if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
+                    uint32_t rec = 0;
+                    if (s < slots_on && j < jn)
+                        rec = (uint32_t)((long)nuc * P.n_gp + nuclide_low<GRID>(P, e_s, (long)w_s, nuc));
+                    if (j < n_steps) s_rec[warp][s][j] = rec;
+                }
+            } else {
+                for (int idx = lane; idx < (kSweepSlots << row_shift); idx += 32) {
+                    const int s = idx >> row_shift, j = idx & ((1 << row_shift) - 1);
+                    const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * s);
+                    double e_s = 0.0;
+                    if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
+                    if (j < n_steps) {
+                        uint32_t rec = 0;
+                        if (s < slots_on && j < jn) {
+                            const int nuc = nucs[j];
+                            rec = (uint32_t)((long)nuc * P.n_gp + nuclide_low<GRID>(P, e_s, (long)w_s, nuc));
+                        }
+                        s_rec[warp][s][j] = rec;
+                    }
                 }
             }
         }
         __syncwarp();
 
-        // ---- software-pipelined gather -------------------------------------------------------
+        // ---- software-pipelined gather: no predication, padded steps multiply by 0 ----------
         const uint32_t *my_rec = s_rec[warp][slot];
-        const int c0 = S.first + S.j_begin;
+        const int ci = S.mat * kConcStride + S.j_begin;
         Quarter A0[kSweepUnroll], A1[kSweepUnroll];
 #pragma unroll
         for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
-        for (int j0 = 0; j0 < n_steps; j0 += 2 * kSweepUnroll) {
+        int j0 = 0;
+        for (; j0 + 2 * kSweepUnroll < n_steps; j0 += 2 * kSweepUnroll) {
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++) A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
+            for (int u = 0; u < kSweepUnroll; u++)
+                A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++) {
-                const int j = j0 + u;
-                sweep_step(A0[u], e, j < jn ? c_mat_conc[c0 + j] : 0.0, f_src, acc_x, acc_y);
-            }
-            if (j0 + 2 * kSweepUnroll < n_steps) {
+            for (int u = 0; u < kSweepUnroll; u++)
+                sweep_step(A0[u], e, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
 #pragma unroll
-                for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
-            }
+            for (int u = 0; u < kSweepUnroll; u++)
+                A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++) {
-                const int j = j0 + kSweepUnroll + u;
-                sweep_step(A1[u], e, j < jn ? c_mat_conc[c0 + j] : 0.0, f_src, acc_x, acc_y);
-            }
+            for (int u = 0; u < kSweepUnroll; u++)
+                sweep_step(A1[u], e, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+        }
+        {   // last iteration: nothing left to prefetch
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++)
+                A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++)
+                sweep_step(A0[u], e, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++)
+                sweep_step(A1[u], e, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
         }
 
         if (!A.last_window) {
@@ -543,7 +603,7 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             const double v[5] = {acc_x, acc_y, q1x, q1y, q2x};
             double gap;
             const int am = argmax5(v, gap);
-            my_sum += (unsigned long long)(am + 1);
+            my_sum += (unsigned int)(am + 1);
             my_count += 1;
             if (sink.macro_out) {
                 const long id = A.sample_id ? (long)A.sample_id[t] : t;
