@@ -55,8 +55,9 @@ int env_int(const char *name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// device counters: [0,16) batch counters of the event kernel, [16,32) partition cursors
-enum { kNumCounters = 32, kCursorBase = 16 };
+// device counters: [0,16) batch counters of the event kernel, then 16 partition cursors per chunk;
+// histogram: 16 material counters per chunk (a run uses chunk 0; host-sample calls are pipelined in chunks)
+enum { kMaxChunks = 8, kCursorBase = 16, kNumCounters = kCursorBase + 16 * kMaxChunks, kNumHist = 16 * kMaxChunks };
 enum { EV_START = 0, EV_SAMPLED, EV_SORTED, EV_LOOKED_UP, EV_DONE, EV_COUNT };
 
 struct DeviceState {
@@ -96,6 +97,8 @@ struct DeviceState {
     double *dump_macro = nullptr;          // staging for macro_xs output
     long dump_capacity = 0;
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaStream_t copy_stream = nullptr;    // host->device copies of a host-sample call overlap its compute
+    cudaEvent_t ev_copy[kMaxChunks] = {}, ev_ready = nullptr;
     int launches = 0;
 };
 
@@ -110,6 +113,7 @@ struct xs_gpu_ctx {
     int gather = xs::kTriple;
     int blocks_per_sm = 0;                 // 0 = from occupancy
     int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
+    int e2e_chunks = 0;                    // host-sample pipeline depth (0 = by size)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
@@ -292,7 +296,10 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     // run scratch
     CUDA_TRY(cudaMalloc(&d.accum, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&d.counters, kNumCounters * sizeof(unsigned int)));
-    CUDA_TRY(cudaMalloc(&d.histogram, 16 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&d.histogram, kNumHist * sizeof(unsigned int)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreateWithFlags(&d.ev_copy[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost(&d.h_accum, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&d.h_hist, 16 * sizeof(unsigned int)));
 
@@ -383,19 +390,33 @@ int launch_event(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs
     return XS_OK;
 }
 
-// One launch of the window kernel over `n_seg` segments.
-int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, xs::BatchSink sink)
+// Buffers of one grouped batch of lookups (a whole run, or one chunk of a host-sample call).
+struct GroupedBatch {
+    const double *energy;          // grouped by material
+    const uint32_t *where;
+    const uint32_t *id;            // original sample index per slot (macro_xs dumps)
+    double2 *partial;
+    long offset[XS_NUM_MATERIALS]; // first slot of each material (host copy of the histogram prefix)
+    long count[XS_NUM_MATERIALS];  // lookups per material
+};
+
+// One launch of the window kernel over `a.n_seg` segments.
+int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const GroupedBatch &b, xs::BatchSink sink)
 {
     long groups = 0;
     for (int i = 0; i < a.n_seg; i++) {
-        a.seg[i].group_begin = groups;
-        groups += (a.seg[i].count + xs::kSweepSlots - 1) / xs::kSweepSlots;
+        const int m = a.seg[i].mat;
+        a.seg[i].offset = b.offset[m];
+        a.seg[i].count = (int)b.count[m];
+        a.seg[i].group_begin = (int)groups;
+        groups += (b.count[m] + xs::kSweepSlots - 1) / xs::kSweepSlots;
     }
     if (groups == 0) return XS_OK;
-    a.n_groups = groups;
-    a.energy = d.grp_e;
-    a.where = d.grp_where;
-    a.partial = d.sweep_partial;
+    a.n_groups = (int)groups;
+    a.energy = b.energy;
+    a.where = b.where;
+    a.sample_id = b.id;
+    a.partial = b.partial;
     WindowKernel k = window_kernel(ctx->grid_type);
     int blocks = 0;
     const size_t smem = (size_t)d.P.mat_total * sizeof(int);
@@ -409,46 +430,40 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, xs::BatchS
     return XS_OK;
 }
 
-// Windowed nuclide sweep over lookups grouped by material (grp_e / grp_where / id):
-// `count[m]` lookups of material mats[m] starting at slot `offset[m]`.  Materials that need
-// several windows (fuel) get one launch per window; all single-window materials share one.
-int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const uint32_t *id, int n_mats, const int *mats,
-                 const long *offset, const long *count, xs::BatchSink sink)
+// Windowed nuclide sweep over a grouped batch, for the materials in `mats`.  Materials that
+// need several windows (fuel) get one launch per window; all single-window materials share one.
+int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, int n_mats, const int *mats,
+                 xs::BatchSink sink)
 {
-    const int window = std::min(ctx->window, xs::kMaxWindow);
+    const int quantum = 2 * xs::kSweepUnroll;
+    const int width = std::max(quantum, std::min(ctx->window, xs::kMaxWindow - 8) / quantum * quantum);
     xs::WindowArgs small{};
-    small.sample_id = id;
     small.first_window = small.last_window = 1;
     int rc = XS_OK;
     for (int i = 0; i < n_mats && rc == XS_OK; i++) {
         const int m = mats[i], n = ctx->num_nucs[m];
-        if (count[i] <= 0) continue;
-        // windows of `window` nuclides (a multiple of the gather loop's step quantum); a short
+        // windows of `width` nuclides (a multiple of the gather loop's step quantum); a short
         // remainder is folded into the last window instead of costing a launch of its own
-        const int quantum = 2 * xs::kSweepUnroll;
-        const int width = std::max(quantum, std::min(window, xs::kMaxWindow - 8) / quantum * quantum);
         int passes = (n + width - 1) / width;
         if (passes > 1 && n - (passes - 1) * width <= 8) passes--;
+        if (b.count[m] <= 0) continue;
         if (passes == 1) {
             xs::WindowSegment &sgm = small.seg[small.n_seg++];
-            sgm.offset = offset[i]; sgm.count = count[i]; sgm.first = d.h_mat_first[m];
-            sgm.j_begin = 0; sgm.j_end = n; sgm.mat = m;
+            sgm.mat = m; sgm.first = d.h_mat_first[m]; sgm.j_begin = 0; sgm.j_end = n;
             continue;
         }
         for (int p = 0; p < passes && rc == XS_OK; p++) {
             xs::WindowArgs a{};
-            a.sample_id = id;
             a.n_seg = 1;
-            a.seg[0].offset = offset[i]; a.seg[0].count = count[i]; a.seg[0].first = d.h_mat_first[m];
-            a.seg[0].mat = m;
+            a.seg[0].mat = m; a.seg[0].first = d.h_mat_first[m];
             a.seg[0].j_begin = p * width;
             a.seg[0].j_end = (p == passes - 1) ? n : (p + 1) * width;
             a.first_window = p == 0;
             a.last_window = p == passes - 1;
-            rc = launch_window(ctx, d, a, sink);
+            rc = launch_window(ctx, d, a, b, sink);
         }
     }
-    if (rc == XS_OK && small.n_seg) rc = launch_window(ctx, d, small, sink);
+    if (rc == XS_OK && small.n_seg) rc = launch_window(ctx, d, small, b, sink);
     return rc;
 }
 
@@ -465,12 +480,18 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
     return XS_OK;
 }
 
-// Sorted variants on device-resident samples (samp_e / samp_mat / samp_where / histogram and,
-// for -k 6, key[0] are ready): regroup, then sweep material by material.
-int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long count, xs::BatchSink sink)
+// Sorted variants on device-resident samples (samp_e / samp_mat / samp_where, the material
+// histogram and, for -k 6, key[0] are ready in device memory): regroup, then sweep material by
+// material.  `base` offsets every per-sample buffer (chunks of a host-sample call); `hist` /
+// `cursor` are this batch's device counters.
+int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long base, long count,
+                           unsigned int *hist, unsigned int *cursor, xs::BatchSink sink, bool record_event)
 {
     int rc = XS_OK;
-    const uint32_t *id = nullptr;
+    GroupedBatch b{};
+    b.energy = d.grp_e + base;
+    b.where = d.grp_where + base;
+    b.partial = d.sweep_partial + 3 * base;
     if (kernel_id == 6) {
         // optimization 6 (cuda/Simulation.cu:1024-1099): sort by (material, energy)
         uint32_t *sorted_perm = nullptr;
@@ -480,30 +501,38 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
         xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e, d.samp_where, count, d.grp_e, d.grp_where);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
-        id = sorted_perm;
+        b.id = sorted_perm;
     } else {
         // optimization 4 (:754-821): group by material; optimization 5 (:895-958): fuel first
         const int tiles = (int)((count + 256 * xs::kPartItems - 1) / (256 * xs::kPartItems));
-        xs::xs_partition_kernel<<<tiles, 256, 0, d.stream>>>(d.samp_e, d.samp_mat, d.samp_where, count, d.histogram,
-                                                           d.counters + kCursorBase, kernel_id == 5, d.grp_e, d.grp_where,
-                                                           kernel_id == 5 ? d.grp_mat : nullptr, d.grp_id);
+        xs::xs_partition_kernel<<<tiles, 256, 0, d.stream>>>(d.samp_e + base, d.samp_mat + base, d.samp_where + base, count,
+                                                           hist, cursor, kernel_id == 5, d.grp_e + base, d.grp_where + base,
+                                                           kernel_id == 5 ? d.grp_mat + base : nullptr, d.grp_id + base);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
-        id = d.grp_id;
+        b.id = d.grp_id + base;
     }
-    CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
-    // group sizes: the sampler's histogram (device -> pinned host; the launches below need them)
-    CUDA_TRY(cudaMemcpyAsync(d.h_hist, d.histogram, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
+    if (record_event) CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+    // group sizes: the sampler's histogram (64 bytes device -> pinned host; the window launches
+    // below take slot ranges as kernel arguments, which measured 5 % faster than deriving them
+    // on the device)
+    CUDA_TRY(cudaMemcpyAsync(d.h_hist, hist, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
+    long offset = 0;
+    for (int m = 0; m < XS_NUM_MATERIALS; m++) {
+        b.offset[m] = offset;
+        b.count[m] = d.h_hist[m];
+        offset += d.h_hist[m];
+    }
     if (kernel_id == 5) {
-        const long n_fuel = d.h_hist[0];
+        // fuel -> windowed sweep; the other 11 materials stay mixed -> one in-order launch
         const int fuel = 0;
-        const long zero = 0;
-        rc = launch_sweep(ctx, d, id, 1, &fuel, &zero, &n_fuel, sink);
+        rc = launch_sweep(ctx, d, b, 1, &fuel, sink);
+        const long n_fuel = d.h_hist[0];
         if (rc == XS_OK && count > n_fuel) {
             xs::BatchSource rest{};
-            rest.energy = d.grp_e + n_fuel;
-            rest.mat = d.grp_mat + n_fuel;
+            rest.energy = d.grp_e + base + n_fuel;
+            rest.mat = d.grp_mat + base + n_fuel;
             rest.count = count - n_fuel;
             rest.mat_lo = 0; rest.mat_hi = XS_NUM_MATERIALS - 1;
             rc = launch_event(ctx, d, rest, sink, 1);
@@ -511,12 +540,8 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
         return rc;
     }
     int mats[XS_NUM_MATERIALS];
-    long offs[XS_NUM_MATERIALS], cnts[XS_NUM_MATERIALS], offset = 0;
-    for (int m = 0; m < XS_NUM_MATERIALS; m++) {
-        mats[m] = m; offs[m] = offset; cnts[m] = d.h_hist[m];
-        offset += d.h_hist[m];
-    }
-    return launch_sweep(ctx, d, id, XS_NUM_MATERIALS, mats, offs, cnts, sink);
+    for (int m = 0; m < XS_NUM_MATERIALS; m++) mats[m] = m;
+    return launch_sweep(ctx, d, b, XS_NUM_MATERIALS, mats, sink);
 }
 
 // One device's share of an event-mode run: ids [first_id, first_id + count).
@@ -527,7 +552,7 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
     CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
     CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.histogram, 0, 16 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
 
     xs::BatchSink sink{};
     sink.accum = d.accum;
@@ -569,7 +594,7 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
                 if (rc == XS_OK) rc = launch_event(ctx, d, src, sink, 1);
             }
         } else {
-            rc = enqueue_grouped_lookup(ctx, d, kernel_id, count, sink);
+            rc = enqueue_grouped_lookup(ctx, d, kernel_id, 0, count, d.histogram, d.counters + kCursorBase, sink, true);
         }
     }
     if (rc != XS_OK) return rc;
@@ -690,6 +715,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->gather = env_int("XSB200_GATHER", xs::kTriple) ? xs::kTriple : xs::kLanePerNuclide;
     ctx->blocks_per_sm = env_int("XSB200_BLOCKS_PER_SM", 0);
     ctx->sweep = env_int("XSB200_SWEEP", 1);
+    ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
@@ -779,26 +805,45 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         CUDA_TRY(cudaSetDevice(d.device));
         d.launches = 0;
         CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-        CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-        CUDA_TRY(cudaMemcpyAsync(d.samp_mat, h_mat + lo, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
         CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
         CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
-        CUDA_TRY(cudaMemsetAsync(d.histogram, 0, 16 * sizeof(unsigned int), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
         xs::BatchSink sink{};
         sink.accum = d.accum;
-        sink.macro_out = h_macro_xs_out ? d.dump_macro : nullptr;
         if (ctx->sweep && cnt > 0) {
-            // group by material, then the windowed nuclide sweep (same pipeline as -k 4)
-            const int blocks = (int)std::min<long>((cnt + 255) / 256, (long)d.sm_count * 16);
-            xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, cnt, d.samp_e, d.samp_mat,
-                                                             d.samp_where, d.histogram);
-            CUDA_TRY(cudaGetLastError());
-            d.launches++;
-            CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
-            rc = enqueue_grouped_lookup(ctx, d, 4, cnt, sink);
+            // Pipelined in chunks: the host->device copy of chunk c+1 (copy stream) overlaps the
+            // row search, grouping and windowed sweep of chunk c (compute stream).  Every chunk
+            // is a complete -k 4 pipeline on its own slice of the buffers (one 64-byte histogram
+            // read-back per chunk; later copies keep running on the copy stream meanwhile).
+            int n_chunks = ctx->e2e_chunks ? ctx->e2e_chunks : (int)std::min<long>(kMaxChunks, std::max<long>(1, cnt / 5000000));
+            CUDA_TRY(cudaEventRecord(d.ev_ready, d.stream));
+            CUDA_TRY(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
+            for (int c = 0; c < n_chunks; c++) {
+                const long c_lo = cnt * c / n_chunks, c_n = cnt * (c + 1) / n_chunks - c_lo;
+                CUDA_TRY(cudaMemcpyAsync(d.samp_e + c_lo, h_energy + lo + c_lo, (size_t)c_n * sizeof(double), cudaMemcpyHostToDevice, d.copy_stream));
+                CUDA_TRY(cudaMemcpyAsync(d.samp_mat + c_lo, h_mat + lo + c_lo, (size_t)c_n * sizeof(int), cudaMemcpyHostToDevice, d.copy_stream));
+                CUDA_TRY(cudaEventRecord(d.ev_copy[c], d.copy_stream));
+            }
+            for (int c = 0; c < n_chunks && rc == XS_OK; c++) {
+                const long c_lo = cnt * c / n_chunks, c_n = cnt * (c + 1) / n_chunks - c_lo;
+                CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_copy[c], 0));
+                const int blocks = (int)std::min<long>((c_n + 255) / 256, (long)d.sm_count * 16);
+                xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
+                                                                 d.samp_where + c_lo, d.histogram + 16 * c);
+                CUDA_TRY(cudaGetLastError());
+                d.launches++;
+                if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+                xs::BatchSink chunk_sink = sink;
+                chunk_sink.macro_out = h_macro_xs_out ? d.dump_macro + 5 * c_lo : nullptr;
+                rc = enqueue_grouped_lookup(ctx, d, 4, c_lo, c_n, d.histogram + 16 * c, d.counters + kCursorBase + 16 * c,
+                                            chunk_sink, c == 0);
+            }
         } else {
+            CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+            CUDA_TRY(cudaMemcpyAsync(d.samp_mat, h_mat + lo, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
             CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
             CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+            sink.macro_out = h_macro_xs_out ? d.dump_macro : nullptr;
             xs::BatchSource src{};
             src.energy = d.samp_e; src.mat = d.samp_mat; src.count = cnt;
             src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
@@ -897,6 +942,9 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         if (d.h_accum) cudaFreeHost(d.h_accum);
         if (d.h_hist) cudaFreeHost(d.h_hist);
         for (int i = 0; i < EV_COUNT; i++) if (d.ev[i]) cudaEventDestroy(d.ev[i]);
+        for (int i = 0; i < kMaxChunks; i++) if (d.ev_copy[i]) cudaEventDestroy(d.ev_copy[i]);
+        if (d.ev_ready) cudaEventDestroy(d.ev_ready);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);
     }
     cudaGetLastError();

@@ -401,18 +401,22 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 #ifndef XS_SWEEP_BLOCKS
 #define XS_SWEEP_BLOCKS 4
 #endif
+#ifndef XS_SWEEP_PREFETCH
+#define XS_SWEEP_PREFETCH 0
+#endif
 constexpr int kSweepUnroll = XS_SWEEP_UNROLL;
+constexpr int kSweepPrefetch = XS_SWEEP_PREFETCH;   // steps ahead of the register pipeline to pull records into L1
 constexpr int kSweepSlots = 8;
 constexpr int kMaxWindow = 64;             // nuclides per window (staging capacity)
 constexpr int kMaxSegments = 12;
 
 struct WindowSegment {
     long offset;               // first slot of this material in the grouped arrays
-    long count;                // lookups of this material
-    long group_begin;          // first warp-group of this segment inside the launch
+    int  count;                // lookups of this material (a batch holds < 2^31)
+    int  group_begin;          // first warp-group of this segment inside the launch
+    int  mat;                  // material of this segment
     int  first;                // mat_first[material]
     int  j_begin, j_end;       // nuclide window inside the material's list
-    int  mat;
 };
 
 struct WindowArgs {
@@ -420,13 +424,15 @@ struct WindowArgs {
     const uint32_t *where;     // same order: UEG row / hash bin
     const uint32_t *sample_id; // same order: original sample index (only for macro_xs dumps)
     double2        *partial;   // [3 * slots] partial sums between windows
-    long  n_groups;            // warp-groups in this launch
+    int   n_groups;            // warp-groups in this launch
     int   n_seg;
     int   first_window, last_window;
     WindowSegment seg[kMaxSegments];
 };
 
 struct Quarter { double a, da, b, db; };
+
+XS_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 XS_DEV Quarter ldg_quarter(const double2 *p)
 {
@@ -458,24 +464,25 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     extern __shared__ int s_nuc[];                           // [mat_total] nuclide ids of all materials
     for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
     __syncthreads();
+    const int n_groups = A.n_groups;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = lane >> 2, quarter = lane & 3;
     const int f_src = lane | 3;
     const double2 *my_pairs = P.pairs + 2 * quarter;
-    const long warp_global = (long)blockIdx.x * kWarpsPerBlock + warp;
-    const long warp_stride = (long)gridDim.x * kWarpsPerBlock;
+    const int warp_global = blockIdx.x * kWarpsPerBlock + warp;
+    const int warp_stride = gridDim.x * kWarpsPerBlock;
     unsigned int my_sum = 0, my_count = 0;                   // per thread: far below 2^32
 
     // energy / row of the group after this one are requested one iteration ahead
     double e_next = 0.5;
     uint32_t where_next = 0;
     {
-        const long g0 = warp_global;
-        if (g0 < A.n_groups) {
+        const int g0 = warp_global;
+        if (g0 < n_groups) {
             int sg = 0;
             while (sg + 1 < A.n_seg && g0 >= A.seg[sg + 1].group_begin) sg++;
-            const long in_seg = (g0 - A.seg[sg].group_begin) * kSweepSlots + slot;
+            const int in_seg = (g0 - A.seg[sg].group_begin) * kSweepSlots + slot;
             if (in_seg < A.seg[sg].count) {
                 e_next = A.energy[A.seg[sg].offset + in_seg];
                 where_next = A.where[A.seg[sg].offset + in_seg];
@@ -483,13 +490,13 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         }
     }
 
-    for (long g = warp_global; g < A.n_groups; g += warp_stride) {
-        int sg = 0;                                          // warp-uniform segment lookup
-        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;
+    int sg = 0;                                              // segments are visited in order
+    for (int g = warp_global; g < n_groups; g += warp_stride) {
+        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;      // warp-uniform
         const WindowSegment &S = A.seg[sg];
-        const long in_seg = (g - S.group_begin) * kSweepSlots + slot;
-        const long t = S.offset + in_seg;                    // global slot
-        const bool on = in_seg < S.count;
+        const int in_seg = (g - A.seg[sg].group_begin) * kSweepSlots + slot;
+        const long t = A.seg[sg].offset + in_seg;                // global slot
+        const bool on = in_seg < A.seg[sg].count;
         const int jn = S.j_end - S.j_begin;
         const int n_steps = (jn + 2 * kSweepUnroll - 1) / (2 * kSweepUnroll) * (2 * kSweepUnroll);
 
@@ -502,13 +509,13 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             acc_y = part.y;
         }
         {   // prefetch the next group's sample
-            const long gn = g + warp_stride;
+            const int gn = g + warp_stride;
             e_next = 0.5;
             where_next = 0;
-            if (gn < A.n_groups) {
+            if (gn < n_groups) {
                 int sn = sg;
                 while (sn + 1 < A.n_seg && gn >= A.seg[sn + 1].group_begin) sn++;
-                const long in_n = (gn - A.seg[sn].group_begin) * kSweepSlots + slot;
+                const int in_n = (gn - A.seg[sn].group_begin) * kSweepSlots + slot;
                 if (in_n < A.seg[sn].count) {
                     e_next = A.energy[A.seg[sn].offset + in_n];
                     where_next = A.where[A.seg[sn].offset + in_n];
@@ -523,7 +530,7 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         __syncwarp();
         {
             const int row_shift = 32 - __clz(n_steps - 1);           // log2(row_len), n_steps >= 4
-            const int slots_on = (int)min((long)kSweepSlots, S.count - (g - S.group_begin) * kSweepSlots);
+            const int slots_on = min(kSweepSlots, A.seg[sg].count - (g - A.seg[sg].group_begin) * kSweepSlots);
             const uint32_t where32 = (uint32_t)where;
             const int *nucs = s_nuc + S.first + S.j_begin;
             if (row_shift <= 5) {
@@ -567,6 +574,13 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
         int j0 = 0;
         for (; j0 + 2 * kSweepUnroll < n_steps; j0 += 2 * kSweepUnroll) {
+            if (kSweepPrefetch > 0) {
+#pragma unroll
+                for (int u = 0; u < 2 * kSweepUnroll; u++) {
+                    const int jp = j0 + kSweepPrefetch + u;
+                    if (jp < n_steps) prefetch_l1(my_pairs + 8 * (long)my_rec[jp]);
+                }
+            }
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
                 A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
