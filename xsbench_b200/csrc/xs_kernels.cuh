@@ -534,18 +534,32 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             const uint32_t where32 = (uint32_t)where;
             const int *nucs = s_nuc + S.first + S.j_begin;
             if (row_shift <= 5) {
-                // a lane keeps its step j in every round; rounds walk over the slots
+                // a lane keeps its step j in every round; rounds walk over the slots.  All index
+                // loads of the (up to 8) rounds are issued before the first one is consumed.
                 const int j = lane & ((1 << row_shift) - 1);
                 const int nuc = j < jn ? nucs[j] : 0;
                 const int per_round = 32 >> row_shift;
-                for (int s = lane >> row_shift; s < kSweepSlots; s += per_round) {
-                    const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * s);
-                    double e_s = 0.0;
-                    if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
-                    uint32_t rec = 0;
-                    if (s < slots_on && j < jn)
-                        rec = (uint32_t)((long)nuc * P.n_gp + nuclide_low<GRID>(P, e_s, (long)w_s, nuc));
-                    if (j < n_steps) s_rec[warp][s][j] = rec;
+                const int s0 = lane >> row_shift;
+                int low[kSweepSlots];
+#pragma unroll
+                for (int r = 0; r < kSweepSlots; r++) {
+                    const int s = s0 + r * per_round;                       // warp-uniform bound below
+                    low[r] = 0;
+                    if (r * per_round < kSweepSlots) {
+                        const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * (s & (kSweepSlots - 1)));
+                        double e_s = 0.0;
+                        if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * (s & (kSweepSlots - 1)));
+                        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID>(P, e_s, (long)w_s, nuc);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kSweepSlots; r++) {
+                    const int s = s0 + r * per_round;
+                    if (r * per_round < kSweepSlots && j < n_steps) {
+                        uint32_t rec = 0;
+                        if (s < slots_on && j < jn) rec = (uint32_t)((long)nuc * P.n_gp + low[r]);
+                        s_rec[warp][s][j] = rec;
+                    }
                 }
             } else {
                 for (int idx = lane; idx < (kSweepSlots << row_shift); idx += 32) {
