@@ -220,6 +220,20 @@ def test_gather_variants_agree(monkeypatch):
     assert sums[0] == sums[1] == ol.OracleProblem(68, 1000, 0, 500).event(0, 50000, NTHREADS)
 
 
+# ---- huge lookup counts are worked through in bounded passes ------------------------------------------
+def test_multi_pass_runs_match_single_pass(monkeypatch):
+    monkeypatch.setenv("XSB200_MAX_PASS", "30000")
+    p = Problem("small", 1000, "unionized", 500, method="event", lookups=100000)
+    try:
+        for k in (1, 4, 5, 6):
+            inp = xs.make_inputs(size="small", grid="unionized", gridpoints=1000, hash_bins=500, method="event",
+                                 lookups=100000, kernel_id=k)
+            res = p.gpu.run(inp)
+            assert res.verification == 302880 and res.n_lookups == 100000, k
+    finally:
+        p.close()
+
+
 # ---- error behaviour: status codes, never exit() ------------------------------------------------------
 def test_error_codes(small):
     bad_k = xs.make_inputs(size="small", gridpoints=1000, method="event", lookups=10, kernel_id=7,
@@ -248,6 +262,28 @@ def test_official_small_event_full_size():
         assert p.gpu.run(hist).checksum == 941535
     finally:
         p.close()
+
+
+@pytest.mark.slow
+def test_xl_problem_golden_checksum():
+    """BASELINE config 5: -s XL (355 x 238,847 grid points, 116.5 GiB unionized).  Golden value 3377 for
+    -l 1000000 comes from the reference run with -G hash / -G nuclide (checksum is grid-type invariant).
+    Needs ~125 GB of host RAM for the generator and ~140 GB of HBM; skipped on smaller machines."""
+    import torch
+    host_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2**30
+    if host_gb < 150 or torch.cuda.get_device_properties(0).total_memory < 150 * 2**30:
+        pytest.skip("needs 150 GB host RAM and a 180 GB GPU")
+    inp = xs.make_inputs(size="XL", method="event", lookups=1000000)
+    assert inp.n_gridpoints == 238847
+    sd = xs.grid_init_do_not_profile(inp)
+    gpu = xs.move_simulation_data_to_device(inp, sd)
+    xs.free_simulation_data(sd)
+    try:
+        for k in (0, 4):
+            res = gpu.run(xs.make_inputs(size="XL", method="event", lookups=1000000, kernel_id=k))
+            assert res.checksum == 3377 and res.n_lookups == 1000000, k
+    finally:
+        gpu.release()
 
 
 @pytest.mark.slow

@@ -114,6 +114,7 @@ struct xs_gpu_ctx {
     int blocks_per_sm = 0;                 // 0 = from occupancy
     int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
     int e2e_chunks = 0;                    // host-sample pipeline depth (0 = by size)
+    long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
@@ -545,12 +546,33 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
 }
 
 // One device's share of an event-mode run: ids [first_id, first_id + count).
+int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count, bool first_pass);
+
+// Variants that materialise samples (-k >= 1) work through the id range in passes of at most
+// `max_pass` lookups, so the sample / grouping buffers stay bounded (112 B per lookup) however
+// many lookups are requested (BASELINE config 5: 1e9+ lookups).  The verification sum simply
+// accumulates over the passes.
 int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count)
 {
     CUDA_TRY(cudaSetDevice(d.device));
     d.launches = 0;
     CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
     CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    const long max_pass = kernel_id == 0 ? count : ctx->max_pass;
+    int rc = XS_OK;
+    long done = 0;
+    do {
+        const long n = std::min(count - done, std::max<long>(max_pass, 1));
+        rc = enqueue_event_pass(ctx, d, kernel_id, first_id + done, n, done == 0);
+        done += n;
+    } while (rc == XS_OK && done < count);
+    if (rc != XS_OK) return rc;
+    CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
+    return XS_OK;
+}
+
+int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count, bool first_pass)
+{
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
 
@@ -565,18 +587,20 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
 
     if (kernel_id == 0) {
         // baseline semantics (cuda/Simulation.cu:44-99): sample + lookup fused, one launch
-        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
-        CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+        if (first_pass) {
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+        }
         rc = launch_event(ctx, d, src, sink, 0);
     } else {
         const bool sorted = kernel_id == 4 || kernel_id == 5 || kernel_id == 6;
         if ((rc = ensure_sample_buffers(d, count, sorted)) != XS_OK) return rc;
         if ((rc = launch_sample(ctx, d, first_id, count, sorted, kernel_id == 6, sorted)) != XS_OK) return rc;
-        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+        if (first_pass) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
         src.energy = d.samp_e;
         src.mat = d.samp_mat;
         if (!sorted) {
-            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+            if (first_pass) CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
             if (kernel_id == 1) {
                 // optimization 1 (cuda/Simulation.cu:388-439): split sample / lookup
                 rc = launch_event(ctx, d, src, sink, 0);
@@ -594,12 +618,10 @@ int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id,
                 if (rc == XS_OK) rc = launch_event(ctx, d, src, sink, 1);
             }
         } else {
-            rc = enqueue_grouped_lookup(ctx, d, kernel_id, 0, count, d.histogram, d.counters + kCursorBase, sink, true);
+            rc = enqueue_grouped_lookup(ctx, d, kernel_id, 0, count, d.histogram, d.counters + kCursorBase, sink, first_pass);
         }
     }
-    if (rc != XS_OK) return rc;
-    CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
-    return XS_OK;
+    return rc;
 }
 
 int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n_particles, int lookups)
@@ -715,6 +737,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->gather = env_int("XSB200_GATHER", xs::kTriple) ? xs::kTriple : xs::kLanePerNuclide;
     ctx->blocks_per_sm = env_int("XSB200_BLOCKS_PER_SM", 0);
     ctx->sweep = env_int("XSB200_SWEEP", 1);
+    ctx->max_pass = std::max(1024, env_int("XSB200_MAX_PASS", 1 << 26));
     ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
@@ -741,7 +764,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
         // pre-allocate the sample / sort buffers here, not inside the timed region
         const long per_gpu = ((long)in->lookups + n_gpus - 1) / n_gpus;
         for (int g = 0; g < n_gpus && rc == XS_OK; g++)
-            rc = ensure_sample_buffers(ctx->dev[g], per_gpu, in->kernel_id >= 4);
+            rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4);
     }
     if (rc == XS_OK && n_gpus > 1) rc = xs_multi_init(ctx);
     if (rc != XS_OK) {
