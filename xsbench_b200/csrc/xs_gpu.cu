@@ -94,6 +94,8 @@ struct DeviceState {
     int *grp_mat = nullptr;                //   material (fuel/other partition only),
     uint32_t *grp_id = nullptr;            //   original sample index
     double2 *sweep_partial = nullptr;      // [sample_capacity*3] partial sums between windows
+    uint64_t *hist_seed = nullptr;         // history mode: LCG state per particle
+    unsigned char *hist_fwd = nullptr;     // history mode: feedback of the previous lookup
     double *dump_macro = nullptr;          // staging for macro_xs output
     long dump_capacity = 0;
     cudaEvent_t ev[EV_COUNT] = {};
@@ -333,7 +335,8 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); d.key[i] = d.perm[i] = nullptr; }
         cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
-        cudaFree(d.sweep_partial);
+        cudaFree(d.sweep_partial); cudaFree(d.hist_seed); cudaFree(d.hist_fwd);
+        d.hist_seed = nullptr; d.hist_fwd = nullptr;
         d.samp_where = nullptr; d.grp_e = nullptr; d.grp_where = nullptr; d.grp_mat = nullptr; d.grp_id = nullptr;
         d.sweep_partial = nullptr;
         d.samp_e = nullptr; d.samp_mat = nullptr;
@@ -353,6 +356,8 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
         CUDA_TRY(cudaMalloc(&d.grp_mat, cap * sizeof(int)));
         CUDA_TRY(cudaMalloc(&d.grp_id, cap * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc(&d.sweep_partial, cap * 3 * sizeof(double2)));
+        CUDA_TRY(cudaMalloc(&d.hist_seed, cap * sizeof(uint64_t)));
+        CUDA_TRY(cudaMalloc(&d.hist_fwd, cap));
         int rc = xs::sort_scratch_alloc(d.sort, d.sample_capacity);
         if (rc != 0) return set_error(XS_ERR_CUDA, "sort scratch allocation failed");
     }
@@ -624,6 +629,33 @@ int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long firs
     return rc;
 }
 
+// History mode by generations: every generation is an event-style batch (all live particles'
+// current lookups), regrouped by material and swept like -k 4; the feedback that makes the
+// reference's inner loop dependent (n_forward) travels through one byte per particle.
+int enqueue_history_generations(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n_particles, int lookups)
+{
+    int rc = XS_OK;
+    for (long done = 0; done < n_particles && rc == XS_OK; done += ctx->max_pass) {
+        const long n = std::min(n_particles - done, ctx->max_pass);
+        if ((rc = ensure_sample_buffers(d, n, true)) != XS_OK) return rc;
+        const int blocks = (int)std::min<long>((n + 255) / 256, (long)d.sm_count * 16);
+        for (int gen = 0; gen < lookups && rc == XS_OK; gen++) {
+            CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
+            CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
+            xs::xs_history_step_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_particle + done, n, lookups, gen,
+                                                                   d.hist_seed, d.hist_fwd, d.samp_e, d.samp_mat,
+                                                                   d.samp_where, d.histogram);
+            CUDA_TRY(cudaGetLastError());
+            d.launches++;
+            xs::BatchSink sink{};
+            sink.accum = d.accum;
+            sink.fwd_out = d.hist_fwd;
+            rc = enqueue_grouped_lookup(ctx, d, 4, 0, n, d.histogram, d.counters + kCursorBase, sink, false);
+        }
+    }
+    return rc;
+}
+
 int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n_particles, int lookups)
 {
     CUDA_TRY(cudaSetDevice(d.device));
@@ -633,7 +665,10 @@ int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
     CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
-    if (n_particles > 0) {
+    if (n_particles > 0 && ctx->sweep) {
+        int rc = enqueue_history_generations(ctx, d, first_particle, n_particles, lookups);
+        if (rc != XS_OK) return rc;
+    } else if (n_particles > 0) {
         HistoryKernel k = history_kernel(ctx->grid_type, ctx->gather);
         int blocks = 0;
         int rc = persistent_grid(ctx, d, (const void *)k, &blocks);
@@ -960,7 +995,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         xs::sort_scratch_free(d.sort);
         cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
-        cudaFree(d.sweep_partial); cudaFree(d.pairs);
+        cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd);
         cudaFree(d.dump_macro);
         if (d.h_accum) cudaFreeHost(d.h_accum);
         if (d.h_hist) cudaFreeHost(d.h_hist);

@@ -52,6 +52,7 @@ struct BatchSink {
     double *energy_out;        // optional [count]
     int    *mat_out;           // optional [count]
     int    *argmax_out;        // optional [count]
+    unsigned char *fwd_out;    // optional [count]: history mode, #{k : macro_xs[k] > 1.0} per sample id
 };
 
 // Material tables staged in shared memory (compact CSR: 484 entries at "large").
@@ -638,6 +639,13 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 #pragma unroll
                 for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = v[k];
             }
+            if (sink.fwd_out) {            // history mode feedback (openmp-threading/Simulation.c:225-228)
+                const long id = A.sample_id ? (long)A.sample_id[t] : t;
+                int fwd = 0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) fwd += v[k] > 1.0;
+                sink.fwd_out[id] = (unsigned char)fwd;
+            }
         }
     }
     const unsigned long long bs = block_sum(my_sum, s_part);
@@ -707,6 +715,43 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
     }
     __syncthreads();
     if (mat_histogram && threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
+        atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
+}
+
+// History mode, one generation for all particles (openmp-threading/Simulation.c:163-171, 225-233):
+// generation 0 seeds particle p at fast_forward_LCG(1070, p*lookups*2*5); later generations
+// first skip n_forward states (the feedback of the previous lookup), then draw energy and
+// material.  Output goes to the same sample arrays the event-mode sampler fills, so the
+// regrouping + windowed sweep that follow are shared with event mode.
+__global__ void __launch_bounds__(256)
+xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long n_particles, int lookups,
+                       int generation, uint64_t *seeds, const unsigned char *fwd, double *energy, int *mat,
+                       uint32_t *where, unsigned int *mat_histogram)
+{
+    __shared__ unsigned int s_hist[kNumMaterials];
+    if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n_particles; t += stride) {
+        uint64_t s;
+        if (generation == 0) {
+            s = lcg_skip(kStartSeed, (uint64_t)(first_particle + t) * (uint64_t)lookups * 10ULL);
+        } else {
+            s = seeds[t];
+            for (int k = fwd[t]; k > 0; k--) s = lcg_step(s);
+        }
+        s = lcg_step(s);
+        const double e = lcg_to_double(s);
+        s = lcg_step(s);
+        const int m = pick_material(lcg_to_double(s));
+        seeds[t] = s;
+        energy[t] = e;
+        mat[t] = m;
+        where[t] = (uint32_t)locate_rt(P, grid_type, e);
+        atomicAdd(&s_hist[m], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
         atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
 }
 
