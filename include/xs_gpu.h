@@ -186,6 +186,17 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
 int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, int *h_mat_out,
                 double *h_macro_xs_out, int *h_argmax_out);
 
+/*
+ * Indirect (index-carrying) sort, the building block of the sorted variants: sorts bits
+ * [lo_bit, hi_bit) of n 32-bit keys (host) with the library's device radix sort and returns the
+ * permutation (host, n entries): keys[perm[0]] <= keys[perm[1]] <= ... on those bits, stable.
+ * This is the "sort ids, not particle payloads" scheme the reference recommends for real
+ * transport codes (cuda/Simulation.cu:1018-1022) and what -k 6 uses internally with
+ * key = material << 28 | energy prefix.
+ */
+int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit, int hi_bit,
+                     uint32_t *h_perm_out);
+
 /* Use `cuda_stream` (a cudaStream_t) for all work of GPU 0 of this context; NULL = default. */
 int xs_gpu_set_stream(xs_gpu_ctx *ctx, void *cuda_stream);
 

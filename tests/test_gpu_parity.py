@@ -220,6 +220,23 @@ def test_gather_variants_agree(monkeypatch):
     assert sums[0] == sums[1] == ol.OracleProblem(68, 1000, 0, 500).event(0, 50000, NTHREADS)
 
 
+# ---- radix sort: permutation, sortedness, stability ----------------------------------------------------
+@pytest.mark.parametrize("n,lo,hi", [(1, 0, 32), (31, 0, 32), (4096, 0, 32), (4097, 8, 32), (1_000_003, 0, 32),
+                                     (300_000, 28, 32), (300_000, 8, 32), (50_000, 0, 8)])
+def test_radix_sort_properties(small, n, lo, hi):
+    rng = np.random.default_rng(n + lo)
+    keys = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[::7] = keys[0]                                   # plenty of duplicates
+    perm = small.gpu.sort_keys(keys, lo, hi)
+    assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32)), "must be a permutation"
+    mask = np.uint32(((1 << (hi - lo)) - 1) << lo) if hi - lo < 32 else np.uint32(0xffffffff)
+    digits = (keys & mask)[perm]
+    assert np.all(digits[1:] >= digits[:-1]), "sorted on the selected bits"
+    want = np.argsort(keys & mask, kind="stable").astype(np.uint32)
+    assert np.array_equal(perm, want), "stable: equal keys keep their order"
+
+
 # ---- huge lookup counts are worked through in bounded passes ------------------------------------------
 def test_multi_pass_runs_match_single_pass(monkeypatch):
     monkeypatch.setenv("XSB200_MAX_PASS", "30000")

@@ -26,7 +26,7 @@ N_PHASES = 4
 
 #: every symbol include/xs_gpu.h declares
 GPU_SYMBOLS = (
-    "xs_gpu_init", "xs_gpu_run", "xs_gpu_run_range", "xs_gpu_lookup_samples", "xs_gpu_dump",
+    "xs_gpu_init", "xs_gpu_run", "xs_gpu_run_range", "xs_gpu_lookup_samples", "xs_gpu_dump", "xs_gpu_sort_keys",
     "xs_gpu_set_stream", "xs_gpu_finalize", "xs_gpu_get_info", "xs_gpu_last_error", "xs_gpu_version",
 )
 #: every symbol host/xs_host.h declares
@@ -157,6 +157,8 @@ def gpu_lib() -> C.CDLL:
     lib.xs_gpu_lookup_samples.argtypes = [ctx_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.POINTER(GpuResult)]
     lib.xs_gpu_dump.restype = C.c_int
     lib.xs_gpu_dump.argtypes = [ctx_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.xs_gpu_sort_keys.restype = C.c_int
+    lib.xs_gpu_sort_keys.argtypes = [ctx_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
     lib.xs_gpu_set_stream.restype = C.c_int
     lib.xs_gpu_set_stream.argtypes = [ctx_p, C.c_void_p]
     lib.xs_gpu_finalize.restype = C.c_int

@@ -951,6 +951,26 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
     return rc;
 }
 
+int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit, int hi_bit, uint32_t *h_perm_out)
+{
+    if (!ctx || !h_keys || !h_perm_out || n < 0 || lo_bit < 0 || hi_bit > 32 || lo_bit >= hi_bit)
+        return set_error(XS_ERR_ARG, "xs_gpu_sort_keys: bad argument");
+    if (n == 0) return XS_OK;
+    if (n > 0xffffffffL) return set_error(XS_ERR_ARG, "xs_gpu_sort_keys: at most 2^32-1 keys");
+    DeviceState &d = ctx->dev[0];
+    int rc = ensure_sample_buffers(d, n, true);
+    if (rc != XS_OK) return rc;
+    CUDA_TRY(cudaSetDevice(d.device));
+    CUDA_TRY(cudaMemcpyAsync(d.key[0], h_keys, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+    uint32_t *sorted_perm = nullptr;
+    int launches = 0;
+    if (xs::sort_lookups(d.sort, d.key, d.perm, n, lo_bit, hi_bit, 0, d.stream, &sorted_perm, &launches) != 0)
+        return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CUDA_TRY(cudaMemcpyAsync(h_perm_out, sorted_perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    return XS_OK;
+}
+
 int xs_gpu_set_stream(xs_gpu_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return set_error(XS_ERR_ARG, "xs_gpu_set_stream: NULL context");

@@ -170,6 +170,13 @@ class DeviceSimulation:
                                           x.ctypes.data, a.ctypes.data))
         return e, m, x, a
 
+    def sort_keys(self, keys: np.ndarray, lo_bit: int = 0, hi_bit: int = 32) -> np.ndarray:
+        """Permutation that sorts bits [lo_bit, hi_bit) of the u32 keys (stable), computed on the device."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        perm = np.empty(keys.shape[0], dtype=np.uint32)
+        self._check(self._lib.xs_gpu_sort_keys(self._ctx, keys.ctypes.data, keys.shape[0], lo_bit, hi_bit, perm.ctypes.data))
+        return perm
+
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._lib.xs_gpu_set_stream(self._ctx, cuda_stream))
 
