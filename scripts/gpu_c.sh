@@ -1,2 +1,4 @@
 #!/bin/bash
-python scripts/quick_bench.py --method history --kernels 0 XSB200_SWEEP=1 XSB200_SWEEP=0 2>&1 | tail -2
+python -m pytest tests -m "gpu and not slow" -x -q 2>&1 | tail -3
+python scripts/quick_bench.py --kernels 4,6 2>&1 | tail -2
+python scripts/quick_bench.py --method history --kernels 0 2>&1 | tail -1

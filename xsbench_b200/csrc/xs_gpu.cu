@@ -441,17 +441,18 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
 int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, int n_mats, const int *mats,
                  xs::BatchSink sink)
 {
+    // windows of `width` nuclides (a multiple of the gather loop's step quantum, at most 32); a
+    // remainder of up to one quantum is folded into the last window instead of costing a launch
+    // of its own (fuel: 321 = 9 x 32 + 33)
     const int quantum = 2 * xs::kSweepUnroll;
-    const int width = std::max(quantum, std::min(ctx->window, xs::kMaxWindow - 8) / quantum * quantum);
+    const int width = std::max(quantum, std::min(ctx->window, 32) / quantum * quantum);
     xs::WindowArgs small{};
     small.first_window = small.last_window = 1;
     int rc = XS_OK;
     for (int i = 0; i < n_mats && rc == XS_OK; i++) {
         const int m = mats[i], n = ctx->num_nucs[m];
-        // windows of `width` nuclides (a multiple of the gather loop's step quantum); a short
-        // remainder is folded into the last window instead of costing a launch of its own
         int passes = (n + width - 1) / width;
-        if (passes > 1 && n - (passes - 1) * width <= 8) passes--;
+        if (passes > 1 && n - (passes - 1) * width <= xs::kMaxWindow - 32) passes--;
         if (b.count[m] <= 0) continue;
         if (passes == 1) {
             xs::WindowSegment &sgm = small.seg[small.n_seg++];

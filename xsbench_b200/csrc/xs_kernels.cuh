@@ -408,7 +408,7 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 constexpr int kSweepUnroll = XS_SWEEP_UNROLL;
 constexpr int kSweepPrefetch = XS_SWEEP_PREFETCH;   // steps ahead of the register pipeline to pull records into L1
 constexpr int kSweepSlots = 8;
-constexpr int kMaxWindow = 64;             // nuclides per window (staging capacity)
+constexpr int kMaxWindow = 36;             // nuclides per window (staging capacity: 32 + one step quantum)
 constexpr int kMaxSegments = 12;
 
 struct WindowSegment {
@@ -435,6 +435,18 @@ struct Quarter { double a, da, b, db; };
 
 XS_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
+// Asynchronous global->shared copies (LDGSTS): the next group's sample is fetched without
+// tying up registers for the duration of the current group.
+XS_DEV void cp_async_8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+XS_DEV void cp_async_4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+XS_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 XS_DEV Quarter ldg_quarter(const double2 *p)
 {
     Quarter v;
@@ -456,12 +468,45 @@ XS_DEV void sweep_step(const Quarter &v, double e, double conc, int f_src, doubl
     acc_y += (v.b - f * v.db) * conc;
 }
 
+// Resolve the record numbers of one window for the 8 lookups of a warp.  The 8 x n_steps
+// (slot, step) pairs are spread over the 32 lanes, ROW = 2^ROW_SHIFT (>= n_steps) pairs per
+// slot: a 4-nuclide material needs one round, a 32-nuclide window eight.  A lane keeps its step
+// j in every round; rounds walk over the slots.  All index loads are issued before the first
+// one is consumed.  Steps [jn, n_steps) are padding: record 0 (concentration 0).
+template <int GRID, int ROW_SHIFT>
+XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1], const int *nucs, int jn, int n_steps,
+                          int slots_on, uint32_t where32, double e, int lane, int j_off = 0)
+{
+    constexpr int kPerRound = 32 >> ROW_SHIFT;
+    constexpr int kRounds = kSweepSlots / kPerRound;
+    const int j = j_off + (lane & ((1 << ROW_SHIFT) - 1));
+    const int s0 = lane >> ROW_SHIFT;
+    const int nuc = j < jn ? nucs[j] : 0;
+    int low[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const int s = s0 + r * kPerRound;
+        const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * s);
+        double e_s = 0.0;
+        if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
+        low[r] = 0;
+        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID>(P, e_s, (long)w_s, nuc);
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; r++) {
+        const int s = s0 + r * kPerRound;
+        if (j < n_steps) rec_rows[s][j] = (s < slots_on && j < jn) ? (uint32_t)((long)nuc * P.n_gp + low[r]) : 0u;
+    }
+}
+
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_SWEEP_BLOCKS)
 xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 {
     __shared__ unsigned long long s_part[kWarpsPerBlock];
     __shared__ uint32_t s_rec[kWarpsPerBlock][kSweepSlots][kMaxWindow + 1];
+    __shared__ double s_next_e[kBlockThreads];
+    __shared__ uint32_t s_next_where[kBlockThreads];
     extern __shared__ int s_nuc[];                           // [mat_total] nuclide ids of all materials
     for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
     __syncthreads();
@@ -473,23 +518,25 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     const double2 *my_pairs = P.pairs + 2 * quarter;
     const int warp_global = blockIdx.x * kWarpsPerBlock + warp;
     const int warp_stride = gridDim.x * kWarpsPerBlock;
-    unsigned int my_sum = 0, my_count = 0;                   // per thread: far below 2^32
+    unsigned int my_sum = 0;                                 // per thread: far below 2^32
 
-    // energy / row of the group after this one are requested one iteration ahead
-    double e_next = 0.5;
-    uint32_t where_next = 0;
-    {
-        const int g0 = warp_global;
-        if (g0 < n_groups) {
-            int sg = 0;
-            while (sg + 1 < A.n_seg && g0 >= A.seg[sg + 1].group_begin) sg++;
-            const int in_seg = (g0 - A.seg[sg].group_begin) * kSweepSlots + slot;
-            if (in_seg < A.seg[sg].count) {
-                e_next = A.energy[A.seg[sg].offset + in_seg];
-                where_next = A.where[A.seg[sg].offset + in_seg];
+    // The sample (energy, row) of a warp's NEXT group is fetched into shared memory with
+    // cp.async while the current group is processed.
+    auto fetch_sample = [&](int gq, int seg_hint) {
+        bool valid = false;
+        if (gq < n_groups) {
+            int sq = seg_hint;
+            while (sq + 1 < A.n_seg && gq >= A.seg[sq + 1].group_begin) sq++;
+            const int in_q = (gq - A.seg[sq].group_begin) * kSweepSlots + slot;
+            if (in_q < A.seg[sq].count) {
+                valid = true;
+                cp_async_8(&s_next_e[threadIdx.x], A.energy + A.seg[sq].offset + in_q);
+                cp_async_4(&s_next_where[threadIdx.x], A.where + A.seg[sq].offset + in_q);
             }
         }
-    }
+        if (!valid) { s_next_e[threadIdx.x] = 0.5; s_next_where[threadIdx.x] = 0u; }
+    };
+    fetch_sample(warp_global, 0);
 
     int sg = 0;                                              // segments are visited in order
     for (int g = warp_global; g < n_groups; g += warp_stride) {
@@ -501,82 +548,29 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         const int jn = S.j_end - S.j_begin;
         const int n_steps = (jn + 2 * kSweepUnroll - 1) / (2 * kSweepUnroll) * (2 * kSweepUnroll);
 
-        const double e = e_next;
-        const long where = where_next;
+        cp_async_wait_all();
+        const double e = s_next_e[threadIdx.x];
+        const uint32_t where32 = s_next_where[threadIdx.x];
+        fetch_sample(g + warp_stride, sg);                   // next group's sample, asynchronously
         double acc_x = 0.0, acc_y = 0.0;
         if (on && !A.first_window && quarter < 3) {
             const double2 part = A.partial[3 * t + quarter];
             acc_x = part.x;
             acc_y = part.y;
         }
-        {   // prefetch the next group's sample
-            const int gn = g + warp_stride;
-            e_next = 0.5;
-            where_next = 0;
-            if (gn < n_groups) {
-                int sn = sg;
-                while (sn + 1 < A.n_seg && gn >= A.seg[sn + 1].group_begin) sn++;
-                const int in_n = (gn - A.seg[sn].group_begin) * kSweepSlots + slot;
-                if (in_n < A.seg[sn].count) {
-                    e_next = A.energy[A.seg[sn].offset + in_n];
-                    where_next = A.where[A.seg[sn].offset + in_n];
-                }
-            }
-        }
 
         // ---- resolve the record numbers of the window for the 8 lookups of this warp ------
-        // The 8 x n_steps (slot, step) pairs are spread over the 32 lanes, `row_len` (a power
-        // of two >= n_steps) pairs per slot, so a 4-nuclide material needs one round, a
-        // 32-nuclide window eight.  Steps [jn, n_steps) are padding: record 0, concentration 0.
         __syncwarp();
         {
-            const int row_shift = 32 - __clz(n_steps - 1);           // log2(row_len), n_steps >= 4
             const int slots_on = min(kSweepSlots, A.seg[sg].count - (g - A.seg[sg].group_begin) * kSweepSlots);
-            const uint32_t where32 = (uint32_t)where;
             const int *nucs = s_nuc + S.first + S.j_begin;
-            if (row_shift <= 5) {
-                // a lane keeps its step j in every round; rounds walk over the slots.  All index
-                // loads of the (up to 8) rounds are issued before the first one is consumed.
-                const int j = lane & ((1 << row_shift) - 1);
-                const int nuc = j < jn ? nucs[j] : 0;
-                const int per_round = 32 >> row_shift;
-                const int s0 = lane >> row_shift;
-                int low[kSweepSlots];
-#pragma unroll
-                for (int r = 0; r < kSweepSlots; r++) {
-                    const int s = s0 + r * per_round;                       // warp-uniform bound below
-                    low[r] = 0;
-                    if (r * per_round < kSweepSlots) {
-                        const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * (s & (kSweepSlots - 1)));
-                        double e_s = 0.0;
-                        if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * (s & (kSweepSlots - 1)));
-                        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID>(P, e_s, (long)w_s, nuc);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < kSweepSlots; r++) {
-                    const int s = s0 + r * per_round;
-                    if (r * per_round < kSweepSlots && j < n_steps) {
-                        uint32_t rec = 0;
-                        if (s < slots_on && j < jn) rec = (uint32_t)((long)nuc * P.n_gp + low[r]);
-                        s_rec[warp][s][j] = rec;
-                    }
-                }
-            } else {
-                for (int idx = lane; idx < (kSweepSlots << row_shift); idx += 32) {
-                    const int s = idx >> row_shift, j = idx & ((1 << row_shift) - 1);
-                    const uint32_t w_s = __shfl_sync(kFullMask, where32, 4 * s);
-                    double e_s = 0.0;
-                    if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
-                    if (j < n_steps) {
-                        uint32_t rec = 0;
-                        if (s < slots_on && j < jn) {
-                            const int nuc = nucs[j];
-                            rec = (uint32_t)((long)nuc * P.n_gp + nuclide_low<GRID>(P, e_s, (long)w_s, nuc));
-                        }
-                        s_rec[warp][s][j] = rec;
-                    }
-                }
+            if (n_steps <= 4)       stage_records<GRID, 2>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
+            else if (n_steps <= 8)  stage_records<GRID, 3>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
+            else if (n_steps <= 16) stage_records<GRID, 4>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
+            else {
+                stage_records<GRID, 5>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
+                if (n_steps > 32)   // a folded remainder: steps 32..35
+                    stage_records<GRID, 2>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane, 32);
             }
         }
         __syncwarp();
@@ -633,7 +627,6 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             double gap;
             const int am = argmax5(v, gap);
             my_sum += (unsigned int)(am + 1);
-            my_count += 1;
             if (sink.macro_out) {
                 const long id = A.sample_id ? (long)A.sample_id[t] : t;
 #pragma unroll
@@ -649,10 +642,13 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         }
     }
     const unsigned long long bs = block_sum(my_sum, s_part);
-    const unsigned long long bc = block_sum(my_count, s_part);
-    if (threadIdx.x == 0 && bc) {
-        atomicAdd(sink.accum, bs);
-        atomicAdd(sink.accum + 1, bc);
+    if (threadIdx.x == 0) {
+        if (bs) atomicAdd(sink.accum, bs);
+        if (blockIdx.x == 0 && A.last_window) {              // lookups completed by this launch
+            unsigned long long done = 0;
+            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
+            atomicAdd(sink.accum + 1, done);
+        }
     }
 }
 
