@@ -195,22 +195,28 @@ XS_DEV int bucket_of(double e, double scale, int n_buckets)
     return b < 0 ? 0 : (b >= n_buckets ? n_buckets - 1 : b);
 }
 
-XS_DEV long ueg_row(const Problem &P, double e)
+// STREAM = true : probes are loaded evict_first (in-order kernels: protect the grid's L2 share);
+// STREAM = false: default policy (sampler kernels run alone, the 40 MB of bucket table + UEG
+//                 then stay in L2 and only their first touch reaches DRAM).
+template <bool STREAM>
+XS_DEV long ueg_row_t(const Problem &P, double e)
 {
     const int b = bucket_of(e, P.bucket_scale, P.n_buckets);
-    long lo = ldg_search_u32(P.ueg_bucket + b);          // rows [lo, hi) are in bucket b
-    long hi = ldg_search_u32(P.ueg_bucket + b + 1);
+    long lo = STREAM ? ldg_search_u32(P.ueg_bucket + b) : __ldg(P.ueg_bucket + b);   // rows [lo, hi) are in bucket b
+    long hi = STREAM ? ldg_search_u32(P.ueg_bucket + b + 1) : __ldg(P.ueg_bucket + b + 1);
     // upper_bound within [lo, hi): first row with ueg > e
     while (hi - lo > 4) {
         const long mid = lo + (hi - lo) / 2;
-        if (ldg_search_f64(P.ueg + mid) > e) hi = mid; else lo = mid + 1;
+        const double u = STREAM ? ldg_search_f64(P.ueg + mid) : __ldg(P.ueg + mid);
+        if (u > e) hi = mid; else lo = mid + 1;
     }
-    while (lo < hi && !(ldg_search_f64(P.ueg + lo) > e)) lo++;
+    while (lo < hi && !((STREAM ? ldg_search_f64(P.ueg + lo) : __ldg(P.ueg + lo)) > e)) lo++;
     long row = lo - 1;
     if (row < 0) row = 0;
     if (row > P.n_ueg - 2) row = P.n_ueg - 2;
     return row;
 }
+XS_DEV long ueg_row(const Problem &P, double e) { return ueg_row_t<true>(P, e); }
 
 // grid_search_nuclide on the energy field of one nuclide's points (48-byte stride).
 XS_DEV int search_nuclide(const double2 *g, double e, int lo, int hi)
@@ -265,9 +271,9 @@ XS_DEV long locate(const Problem &P, double e)
     return -1;
 }
 
-XS_DEV long locate_rt(const Problem &P, int grid_type, double e)
+XS_DEV long locate_rt(const Problem &P, int grid_type, double e)      // sampler kernels
 {
-    if (grid_type == kUnionized) return ueg_row(P, e);
+    if (grid_type == kUnionized) return ueg_row_t<false>(P, e);
     if (grid_type == kHash)      return hash_bin(P, e);
     return 0;
 }
