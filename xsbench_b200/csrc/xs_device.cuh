@@ -231,26 +231,45 @@ XS_DEV int search_nuclide(const double2 *g, double e, int lo, int hi)
 // Index of the lower bounding grid point of nuclide `nuc` for energy e.
 //   unionized: index_grid[row][nuc]; nuclide: full search; hash: bracketed search.
 // `where` is the UEG row (unionized) or the hash bin (hash); unused for nuclide.
-template <int GRID>
+// Energy of grid point k of a nuclide, read from the PAIR RECORDS (record r = base + k holds
+// lo.E of point k in chunk 5 and hi.E = energy of point k+1 in chunk 6).  The searches of the
+// sweep path probe the same 128-byte lines the gather reads afterwards.
+XS_DEV double rec_energy(const Problem &P, long base, int k)
+{
+    const double2 *p = (k < P.n_gp - 1) ? P.pairs + 8 * (base + k) + 5 : P.pairs + 8 * (base + k - 1) + 6;
+    return __ldg(&p->x);
+}
+XS_DEV int search_nuclide_rec(const Problem &P, long base, double e, int lo, int hi)
+{
+    while (hi - lo > 1) {
+        const int mid = lo + (hi - lo) / 2;
+        if (rec_energy(P, base, mid) > e) hi = mid; else lo = mid;
+    }
+    return lo;
+}
+
+// REC = false: energies from the reference-layout grid; REC = true: from the pair records.
+template <int GRID, bool REC = false>
 XS_DEV int nuclide_low(const Problem &P, double e, long where, int nuc)
 {
     const int last = P.n_gp - 1;
+    const long base = (long)nuc * P.n_gp;
+    const double2 *g = P.grid + 3 * base;
     int low;
     if (GRID == kUnionized) {
         low = ldg_index_stream(P.index_grid + where * P.n_iso + nuc);
     } else if (GRID == kNuclide) {
-        low = search_nuclide(P.grid + 3 * (long)nuc * P.n_gp, e, 0, last);
+        low = REC ? search_nuclide_rec(P, base, e, 0, last) : search_nuclide(g, e, 0, last);
     } else {
-        const double2 *g = P.grid + 3 * (long)nuc * P.n_gp;
         const int u_lo = ldg_index_keep(P.index_grid + where * P.n_iso + nuc);
         const int u_hi = (where == P.hash_bins - 1)
                              ? last
                              : ldg_index_keep(P.index_grid + (where + 1) * P.n_iso + nuc) + 1;
-        const double e_lo = ldg_grid_energy(g + 3 * (long)u_lo);
-        const double e_hi = ldg_grid_energy(g + 3 * (long)u_hi);
+        const double e_lo = REC ? rec_energy(P, base, u_lo) : ldg_grid_energy(g + 3 * (long)u_lo);
+        const double e_hi = REC ? rec_energy(P, base, u_hi) : ldg_grid_energy(g + 3 * (long)u_hi);
         if (e <= e_lo)      low = 0;
         else if (e >= e_hi) low = last;
-        else                low = search_nuclide(g, e, u_lo, u_hi);
+        else                low = REC ? search_nuclide_rec(P, base, e, u_lo, u_hi) : search_nuclide(g, e, u_lo, u_hi);
     }
     return low == last ? last - 1 : low;
 }

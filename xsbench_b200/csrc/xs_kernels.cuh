@@ -380,7 +380,7 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 // 128-byte line per (nuclide, k), holding for grid points lo = k and hi = k+1:
 //     quarter 0: hi.total, hi.total-lo.total, hi.elastic, hi.elastic-lo.elastic
 //     quarter 1: hi.absorbtion, d(absorbtion), hi.fission, d(fission)
-//     quarter 2: hi.nu_fission, d(nu_fission), 0, 0
+//     quarter 2: hi.nu_fission, d(nu_fission), lo.energy, 0
 //     quarter 3: hi.energy, d = hi.energy-lo.energy, 1/d, 0
 // The differences are the reference's own intermediate values (hi - lo rounded once), so
 // xs = hi - f*(hi-lo) is computed with the reference's roundings.
@@ -490,7 +490,7 @@ XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1]
         double e_s = 0.0;
         if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
         low[r] = 0;
-        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID>(P, e_s, (long)w_s, nuc);
+        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID, GRID == kHash>(P, e_s, (long)w_s, nuc);   // hash: probe the records (measured faster); nuclide: the compact grid
     }
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
@@ -670,6 +670,7 @@ __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp
             out[2] = make_double2(h1.y, h1.y - l1.y);        // absorbtion
             out[3] = make_double2(h2.x, h2.x - l2.x);        // fission
             out[4] = make_double2(h2.y, h2.y - l2.y);        // nu_fission
+            out[5] = make_double2(l0.x, 0.0);                // lo.E (probed by the record searches)
             out[6] = make_double2(h0.x, d);                  // hi.E, d
             out[7] = make_double2(1.0 / d, 0.0);             // correctly rounded reciprocal
         }
