@@ -33,6 +33,7 @@ constexpr double kTieGuard = 1e-10;      // relative gap below which order of su
 //                     lanes per nuclide and kBigUnroll x 10 nuclides in flight (phase B,
 //                     warp_macro_big).
 constexpr int kLanePerNuclide = 0, kTriple = 1;
+constexpr int kBigUnroll = 4;            // phase B: 4 x 10 nuclides in flight per warp
 constexpr int kSmallMax = 32;            // materials with at most this many nuclides go to phase A
 
 // Where a batch's (energy, material) pairs come from.
@@ -60,6 +61,7 @@ struct SharedTables {
     int    first[kNumMaterials + 1];
     int    pad[3];
     double exchange[kWarpsPerBlock][8];   // per-warp scratch for the 3-lane reduction
+    int    stage[kWarpsPerBlock][2 * 10 * 4];     // per-warp hand-over of resolved grid points (phase B)
 };
 
 XS_DEV void stage_tables(const Problem &P, SharedTables &T, int *s_nuc, double *s_conc)
@@ -166,32 +168,40 @@ XS_DEV void lane_macro_small(const Problem &P, const int *s_nuc, const double *s
 // a nuclide -- lane c loads 16-byte chunk c of the low and of the high grid point, so one
 // load instruction touches 48 contiguous bytes per nuclide (about 1.3 L1 wavefronts per
 // nuclide and instruction instead of 6 for one lane per nuclide).  U steps of 10 nuclides are
-// in flight per iteration (2U loads per lane) and the index entries of the next iteration are
-// requested before the current data is consumed.  e / where / (first, n) are warp-uniform;
-// on return every lane holds the same five sums.
+// in flight per iteration (2U loads per lane).  The lower grid-point index of every nuclide is
+// resolved LANE-PARALLEL (one nuclide per lane: 32 index loads / searches in flight, coalesced
+// index-row segments) one iteration ahead and handed over through `stage` (2 x 10U ints of
+// shared memory per warp).  e / where / (first, n) are warp-uniform; on return every lane
+// holds the same five sums.
 // ---------------------------------------------------------------------------------------
 template <int GRID, int U>
 XS_DEV void warp_macro_big(const Problem &P, const int *s_nuc, const double *s_conc, int first, int n,
                            double e, long where, int lane, double *exchange /* 8 doubles, per warp */,
-                           double out[5])
+                           int *stage /* 2 * 10U ints, per warp */, double out[5])
 {
+    constexpr int kPerIter = 10 * U;
     const int slot = lane / 3;                 // 10 nuclides per step; lanes 30,31 idle
     const int chunk = lane - 3 * slot;         // which 16-byte chunk of a grid point
     const bool lane_on = lane < 30;
     const int f_src = lane - chunk;            // lane holding both energies of this slot
     double acc_x = 0.0, acc_y = 0.0;
-    long at[U];                                // chunk index of the low point, -1 = off
 
+    auto resolve = [&](int j0, int *buf) {     // stage[j - j0] = low point of nuclide j, j in [j0, j0+10U)
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        const int j = u * 10 + slot;
-        at[u] = -1;
-        if (lane_on && j < n) {
-            const int nuc = s_nuc[first + j];
-            at[u] = 3 * ((long)nuc * P.n_gp + nuclide_low<GRID>(P, e, where, nuc)) + chunk;
+        for (int r = 0; r < (kPerIter + 31) / 32; r++) {
+            const int i = r * 32 + lane;
+            if (i < kPerIter && j0 + i < n) {
+                const int nuc = s_nuc[first + j0 + i];
+                buf[i] = nuc * P.n_gp + nuclide_low<GRID>(P, e, where, nuc);      // < 2^31 up to XXL
+            }
         }
-    }
-    for (int j0 = 0; j0 < n; j0 += 10 * U) {
+    };
+    __syncwarp();
+    resolve(0, stage);
+    __syncwarp();
+    int it = 0;
+    for (int j0 = 0; j0 < n; j0 += kPerIter, it ^= 1) {
+        const int *cur = stage + it * kPerIter;
         double2 lo[U], hi[U];
         double conc[U];
 #pragma unroll
@@ -199,21 +209,15 @@ XS_DEV void warp_macro_big(const Problem &P, const int *s_nuc, const double *s_c
             lo[u] = make_double2(0.0, 0.0);
             hi[u] = make_double2(1.0, 0.0);
             conc[u] = 0.0;
-            if (at[u] >= 0) {
-                lo[u] = ldg_grid(P.grid + at[u]);
-                hi[u] = ldg_grid(P.grid + at[u] + 3);
-                conc[u] = s_conc[first + j0 + u * 10 + slot];
+            const int i = u * 10 + slot;
+            if (lane_on && j0 + i < n) {
+                const double2 *p = P.grid + 3 * (long)cur[i] + chunk;
+                lo[u] = ldg_grid(p);
+                hi[u] = ldg_grid(p + 3);
+                conc[u] = s_conc[first + j0 + i];
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {          // next iteration's index entries
-            const int j = j0 + 10 * U + u * 10 + slot;
-            at[u] = -1;
-            if (lane_on && j < n) {
-                const int nuc = s_nuc[first + j];
-                at[u] = 3 * ((long)nuc * P.n_gp + nuclide_low<GRID>(P, e, where, nuc)) + chunk;
-            }
-        }
+        if (j0 + kPerIter < n) resolve(j0 + kPerIter, stage + (it ^ 1) * kPerIter);   // next iteration's points
         double f[U];
 #pragma unroll
         for (int u = 0; u < U; u++) f[u] = (hi[u].x - e) / (hi[u].x - lo[u].x);   // used from chunk 0
@@ -223,6 +227,7 @@ XS_DEV void warp_macro_big(const Problem &P, const int *s_nuc, const double *s_c
             acc_x += lerp_xs(lo[u].x, hi[u].x, fu) * conc[u];                     // conc == 0 when off
             acc_y += lerp_xs(lo[u].y, hi[u].y, fu) * conc[u];
         }
+        __syncwarp();
     }
     // Sum the 10 slots: lanes 0,1,2 end up with the totals of chunk 0,1,2.
 #pragma unroll
@@ -239,13 +244,12 @@ XS_DEV void warp_macro_big(const Problem &P, const int *s_nuc, const double *s_c
     for (int k = 0; k < 5; k++) out[k] = exchange[k + 1];
 }
 
-constexpr int kBigUnroll = 4;
 
 template <int GRID, int GATHER>
 XS_DEV void warp_macro(const Problem &P, const int *s_nuc, const double *s_conc, int first, int n,
-                       double e, long where, int lane, double *exchange, double out[5])
+                       double e, long where, int lane, double *exchange, int *stage, double out[5])
 {
-    if (GATHER == kTriple) warp_macro_big<GRID, kBigUnroll>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, out);
+    if (GATHER == kTriple) warp_macro_big<GRID, kBigUnroll>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, stage, out);
     else                   warp_macro_lane_per_nuclide<GRID>(P, s_nuc, s_conc, first, n, e, where, lane, out);
 }
 
@@ -326,7 +330,7 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
             const long where = __shfl_sync(kFullMask, where_l, i);
             const int first = T.first[mat], n = T.first[mat + 1] - first;
             double out[5];
-            warp_macro<GRID, GATHER>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, out);
+            warp_macro<GRID, GATHER>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, T.stage[warp], out);
             if (lane == i) {
 #pragma unroll
                 for (int k = 0; k < 5; k++) mine[k] = out[k];
@@ -869,7 +873,7 @@ xs_history_kernel(const Problem P, long first_particle, long n_particles, int lo
             const long where = locate<GRID>(P, e);
             const int first = T.first[mat], n = T.first[mat + 1] - first;
             double out[5];
-            warp_macro<GRID, GATHER>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, out);
+            warp_macro<GRID, GATHER>(P, s_nuc, s_conc, first, n, e, where, lane, exchange, T.stage[warp], out);
             double gap;
             int am = argmax5(out, gap);
             bool redo = gap <= kTieGuard;
