@@ -142,6 +142,10 @@ typedef struct {
  *   n_gpus   : 1..8 GPUs of this node driven from the calling thread; the grid is replicated
  *              on each (peer copy from GPU 0), lookups are partitioned, and the only
  *              collective is an all-reduce of {verification, n_lookups}.
+ * Device-side generation: if host_sd->nuclide_grid, ->unionized_energy_array and ->index_grid
+ * are all NULL (num_nucs / mats / concs / max_num_nucs still given), the synthetic problem of
+ * grid_init_do_not_profile is built directly in device memory, byte-identical to the host
+ * generator -- nothing large exists on the host or crosses PCIe (XL: 116 GB).
  * Also pre-allocates every scratch buffer (the reference allocates its sample buffers inside
  * the timed region: cuda/Simulation.cu:401-409), builds search-acceleration tables and sets
  * the L2 persistence window.  Device used: the calling thread's current CUDA device, then
@@ -196,6 +200,16 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
  */
 int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit, int hi_bit,
                      uint32_t *h_perm_out);
+
+/*
+ * Copy a range of one of the device-resident problem arrays (reference layout) back to the
+ * host: the device-generated problem can be checked against / saved like a host-generated one
+ * (cuda/io.cu:443-470 binary_write).  `which` is one of XS_ARRAY_*.
+ */
+#define XS_ARRAY_NUCLIDE_GRID      0
+#define XS_ARRAY_UNIONIZED_ENERGY  1
+#define XS_ARRAY_INDEX_GRID        2
+int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_bytes, void *h_dst);
 
 /* Use `cuda_stream` (a cudaStream_t) for all work of GPU 0 of this context; NULL = default. */
 int xs_gpu_set_stream(xs_gpu_ctx *ctx, void *cuda_stream);

@@ -1,5 +1,4 @@
 #!/bin/bash
-python -m pytest tests -m "gpu and not slow" -x -q 2>&1 | tail -3
-python scripts/quick_bench.py --kernels 0,1 2>&1 | tail -2
-python scripts/quick_bench.py --grid hash --kernels 0 2>&1 | tail -1
-python scripts/quick_bench.py --grid nuclide --kernels 0 2>&1 | tail -1
+python -m pytest tests -m "gpu and not slow" -x -q 2>&1 | tail -5
+python -m pytest tests -m "gpu" -x -q -k "official_large" 2>&1 | tail -3
+xsbench_b200/xsbench -m event -s large -k 4 --device-init --reps 3 2>&1 | grep -E "Building|Allocated|Device time|Lookups/s|checksum"

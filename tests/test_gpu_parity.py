@@ -220,6 +220,30 @@ def test_gather_variants_agree(monkeypatch):
     assert sums[0] == sums[1] == ol.OracleProblem(68, 1000, 0, 500).event(0, 50000, NTHREADS)
 
 
+# ---- device-side generator: byte-identical to the host generator --------------------------------------------
+@pytest.mark.parametrize("size,n_gp,grid,hb", [("small", 1000, "unionized", 10000), ("small", 1000, "hash", 500),
+                                               ("small", 1000, "nuclide", 10000), ("large", 300, "unionized", 10000),
+                                               ("large", 300, "hash", 37), ("small", 2, "unionized", 10000),
+                                               ("small", 5000, "unionized", 10000)])
+def test_device_generator_byte_identical(size, n_gp, grid, hb):
+    inp = xs.make_inputs(size=size, method="event", grid=grid, lookups=50000, gridpoints=n_gp, hash_bins=hb, kernel_id=4)
+    host_sd = xs.grid_init_do_not_profile(inp)
+    host = xs.simulation_arrays(inp, host_sd)
+    mats = xs.materials_only(inp)
+    with xs.move_simulation_data_to_device(inp, mats) as gpu:
+        assert np.array_equal(gpu.read_array("nuclide_grid"), host["nuclide_grid"])
+        if grid == "unionized":
+            assert np.array_equal(gpu.read_array("unionized_energy_array"), host["unionized_energy_array"])
+        if grid != "nuclide":
+            assert np.array_equal(gpu.read_array("index_grid"), host["index_grid"])
+        res = gpu.run()
+        orc = ol.OracleProblem(inp.n_isotopes, n_gp, GRIDS[grid], hb)
+        assert res.verification == orc.event(0, 50000, NTHREADS)
+        orc.close()
+    xs.free_simulation_data(host_sd)
+    xs.free_simulation_data(mats)
+
+
 # ---- radix sort: permutation, sortedness, stability ----------------------------------------------------
 @pytest.mark.parametrize("n,lo,hi", [(1, 0, 32), (31, 0, 32), (4096, 0, 32), (4097, 8, 32), (1_000_003, 0, 32),
                                      (300_000, 28, 32), (300_000, 8, 32), (50_000, 0, 8)])
@@ -309,6 +333,15 @@ def test_official_large_event_full_size():
     inp = xs.make_inputs(size="large", method="event")
     sd = xs.grid_init_do_not_profile(inp)
     gpu = xs.move_simulation_data_to_device(inp, sd)
+    # the same problem built on the device must be byte-identical at full size too
+    mats = xs.materials_only(inp)
+    with xs.move_simulation_data_to_device(inp, mats) as generated:
+        host = xs.simulation_arrays(inp, sd)
+        assert np.array_equal(generated.read_array("unionized_energy_array"), host["unionized_energy_array"])
+        assert np.array_equal(generated.read_array("nuclide_grid"), host["nuclide_grid"])
+        assert np.array_equal(generated.read_array("index_grid"), host["index_grid"])
+        assert generated.run(xs.make_inputs(size="large", method="event", kernel_id=4)).checksum == 952131
+    xs.free_simulation_data(mats)
     xs.free_simulation_data(sd)
     try:
         for k in (0, 1, 4, 6):

@@ -26,13 +26,13 @@ N_PHASES = 4
 
 #: every symbol include/xs_gpu.h declares
 GPU_SYMBOLS = (
-    "xs_gpu_init", "xs_gpu_run", "xs_gpu_run_range", "xs_gpu_lookup_samples", "xs_gpu_dump", "xs_gpu_sort_keys",
+    "xs_gpu_init", "xs_gpu_run", "xs_gpu_run_range", "xs_gpu_lookup_samples", "xs_gpu_dump", "xs_gpu_sort_keys", "xs_gpu_read_array",
     "xs_gpu_set_stream", "xs_gpu_finalize", "xs_gpu_get_info", "xs_gpu_last_error", "xs_gpu_version",
 )
 #: every symbol host/xs_host.h declares
 HOST_SYMBOLS = (
     "LCG_random_double", "fast_forward_LCG", "pick_mat", "xs_material_thresholds", "xs_parse_cli",
-    "read_CLI", "print_CLI_error", "xs_strip_driver_opts", "grid_init_do_not_profile",
+    "read_CLI", "print_CLI_error", "xs_strip_driver_opts", "grid_init_do_not_profile", "xs_materials_only",
     "xs_free_simulation_data", "load_num_nucs", "load_mats", "load_concs", "NGP_compare",
     "double_compare", "estimate_mem_usage", "get_time", "logo", "center_print", "border_print",
     "fancy_int", "print_inputs", "print_results", "xs_expected_checksum", "binary_write", "binary_read",
@@ -78,7 +78,7 @@ class GpuInfo(C.Structure):
 
 
 class DriverOpts(C.Structure):
-    _fields_ = [("gpus", C.c_int), ("reps", C.c_int), ("json", C.c_int), ("dump_xs", C.c_long)]
+    _fields_ = [("gpus", C.c_int), ("reps", C.c_int), ("json", C.c_int), ("dump_xs", C.c_long), ("device_init", C.c_int)]
 
 
 assert C.sizeof(Inputs) == 64 and C.sizeof(NuclideGridPoint) == 48 and C.sizeof(SimulationData) == 128
@@ -112,6 +112,8 @@ def host_lib() -> C.CDLL:
     lib.xs_strip_driver_opts.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(DriverOpts)]
     lib.grid_init_do_not_profile.restype = SimulationData
     lib.grid_init_do_not_profile.argtypes = [Inputs, C.c_int]
+    lib.xs_materials_only.restype = SimulationData
+    lib.xs_materials_only.argtypes = [Inputs]
     lib.xs_free_simulation_data.restype = None
     lib.xs_free_simulation_data.argtypes = [C.POINTER(SimulationData)]
     lib.load_num_nucs.restype = C.POINTER(C.c_int)
@@ -159,6 +161,8 @@ def gpu_lib() -> C.CDLL:
     lib.xs_gpu_dump.argtypes = [ctx_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.xs_gpu_sort_keys.restype = C.c_int
     lib.xs_gpu_sort_keys.argtypes = [ctx_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
+    lib.xs_gpu_read_array.restype = C.c_int
+    lib.xs_gpu_read_array.argtypes = [ctx_p, C.c_int, C.c_long, C.c_long, C.c_void_p]
     lib.xs_gpu_set_stream.restype = C.c_int
     lib.xs_gpu_set_stream.argtypes = [ctx_p, C.c_void_p]
     lib.xs_gpu_finalize.restype = C.c_int

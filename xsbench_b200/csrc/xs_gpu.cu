@@ -21,6 +21,7 @@
 #include "xs_gpu.h"
 #include "xs_kernels.cuh"
 #include "xs_sort.cuh"
+#include "xs_generate.cuh"
 
 namespace {
 
@@ -203,24 +204,22 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         return cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, d.stream);
     };
 
+    const bool generate = !peer && !sd->nuclide_grid;          // build the problem on the device
+
     // nuclide grid (48-byte points, viewed as 16-byte chunks)
     const size_t grid_bytes = (size_t)n_points * sizeof(NuclideGridPoint);
     CUDA_TRY(cudaMalloc(&d.grid, grid_bytes));
-    CUDA_TRY(copy_in(d.grid, sd->nuclide_grid, peer ? peer->grid : nullptr, grid_bytes));
+    if (!generate) CUDA_TRY(copy_in(d.grid, sd->nuclide_grid, peer ? peer->grid : nullptr, grid_bytes));
     d.resident_bytes += grid_bytes;
     P.grid = d.grid;
-    // pair records (B200 layout for the windowed sweep): one 128-byte line per (nuclide, k)
-    const size_t pair_bytes = (size_t)n_points * 8 * sizeof(double2);
-    CUDA_TRY(cudaMalloc(&d.pairs, pair_bytes));
-    xs::xs_build_pairs_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, d.pairs);
-    CUDA_TRY(cudaGetLastError());
-    d.resident_bytes += pair_bytes;
-    P.pairs = d.pairs;
 
     // search structures
+    double *ueg = nullptr;
+    uint32_t *bucket = nullptr;
+    long n_buckets = 0;
     if (ctx->grid_type == XS_UNIONIZED) {
-        const long n_ueg = sd->length_unionized_energy_array;
-        long n_buckets = n_ueg / 2;
+        const long n_ueg = n_points;
+        n_buckets = n_ueg / 2;
         if (n_buckets < 1) n_buckets = 1;
         if (n_buckets > (1L << 24)) n_buckets = 1L << 24;
         n_buckets = env_int("XSB200_BUCKETS", (int)n_buckets);
@@ -228,16 +227,14 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         const size_t ueg_bytes = (size_t)n_ueg * sizeof(double);
         d.hot_bytes = bucket_bytes + ueg_bytes;
         CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
-        uint32_t *bucket = reinterpret_cast<uint32_t *>(d.hot_slab);
-        double *ueg = reinterpret_cast<double *>(d.hot_slab + bucket_bytes);
-        CUDA_TRY(copy_in(ueg, sd->unionized_energy_array,
-                         peer ? peer->hot_slab + bucket_bytes : nullptr, ueg_bytes));
-        xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(
-            ueg, n_ueg, (double)n_buckets, (int)n_buckets, bucket);
-        CUDA_TRY(cudaGetLastError());
-        const size_t index_bytes = (size_t)sd->length_index_grid * sizeof(int);
+        bucket = reinterpret_cast<uint32_t *>(d.hot_slab);
+        ueg = reinterpret_cast<double *>(d.hot_slab + bucket_bytes);
+        const size_t index_bytes = (size_t)n_ueg * (size_t)n_iso * sizeof(int);
         CUDA_TRY(cudaMalloc(&d.index_grid, index_bytes));
-        CUDA_TRY(copy_in(d.index_grid, sd->index_grid, peer ? peer->index_grid : nullptr, index_bytes));
+        if (!generate) {
+            CUDA_TRY(copy_in(ueg, sd->unionized_energy_array, peer ? peer->hot_slab + bucket_bytes : nullptr, ueg_bytes));
+            CUDA_TRY(copy_in(d.index_grid, sd->index_grid, peer ? peer->index_grid : nullptr, index_bytes));
+        }
         d.resident_bytes += d.hot_bytes + index_bytes;
         P.ueg = ueg;
         P.ueg_bucket = bucket;
@@ -246,12 +243,31 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         P.bucket_scale = (double)n_buckets;
         P.index_grid = d.index_grid;
     } else if (ctx->grid_type == XS_HASH) {
-        d.hot_bytes = (size_t)sd->length_index_grid * sizeof(int);
+        d.hot_bytes = (size_t)in->hash_bins * (size_t)n_iso * sizeof(int);
         CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
-        CUDA_TRY(copy_in(d.hot_slab, sd->index_grid, peer ? peer->hot_slab : nullptr, d.hot_bytes));
+        if (!generate) CUDA_TRY(copy_in(d.hot_slab, sd->index_grid, peer ? peer->hot_slab : nullptr, d.hot_bytes));
         d.resident_bytes += d.hot_bytes;
         P.index_grid = reinterpret_cast<const int *>(d.hot_slab);
     }
+    if (generate) {
+        int *index_dst = ctx->grid_type == XS_UNIONIZED ? d.index_grid : reinterpret_cast<int *>(d.hot_slab);
+        const int g = xs::generate_problem(ctx->grid_type, n_iso, n_gp, in->hash_bins, d.grid, ueg, index_dst, d.sm_count, d.stream);
+        if (g == -2)
+            return set_error(XS_ERR_UNSUPP, "device generator: a nuclide holds two equal energies; generate on the host instead");
+        if (g != 0)
+            return set_error(XS_ERR_CUDA, "device generator failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (ctx->grid_type == XS_UNIONIZED) {
+        xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(ueg, n_points, (double)n_buckets, (int)n_buckets, bucket);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // pair records (B200 layout for the windowed sweep): one 128-byte line per (nuclide, k)
+    const size_t pair_bytes = (size_t)n_points * 8 * sizeof(double2);
+    CUDA_TRY(cudaMalloc(&d.pairs, pair_bytes));
+    xs::xs_build_pairs_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, d.pairs);
+    CUDA_TRY(cudaGetLastError());
+    d.resident_bytes += pair_bytes;
+    P.pairs = d.pairs;
 
     // compact (CSR) material tables
     int first[XS_NUM_MATERIALS + 1];
@@ -740,17 +756,24 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     if (n_gpus < 1 || n_gpus > 8) return set_error(XS_ERR_ARG, "xs_gpu_init: n_gpus must be 1..8");
     if (in->grid_type < 0 || in->grid_type > 2) return set_error(XS_ERR_ARG, "xs_gpu_init: bad grid_type %d", in->grid_type);
     if (in->n_isotopes < 1 || in->n_gridpoints < 2) return set_error(XS_ERR_ARG, "xs_gpu_init: bad problem size");
-    if (!sd->nuclide_grid || !sd->num_nucs || !sd->mats || !sd->concs)
-        return set_error(XS_ERR_ARG, "xs_gpu_init: SimulationData has NULL arrays");
-    if (sd->length_nuclide_grid != in->n_isotopes * in->n_gridpoints)
-        return set_error(XS_ERR_ARG, "xs_gpu_init: length_nuclide_grid does not match Inputs");
-    if (in->grid_type == XS_UNIONIZED &&
-        (!sd->unionized_energy_array || !sd->index_grid ||
-         sd->length_index_grid != (long)sd->length_unionized_energy_array * in->n_isotopes))
-        return set_error(XS_ERR_ARG, "xs_gpu_init: unionized grid arrays missing or inconsistent");
-    if (in->grid_type == XS_HASH &&
-        (!sd->index_grid || in->hash_bins < 1 || sd->length_index_grid != (long)in->hash_bins * in->n_isotopes))
-        return set_error(XS_ERR_ARG, "xs_gpu_init: hash grid missing or inconsistent");
+    if (!sd->num_nucs || !sd->mats || !sd->concs)
+        return set_error(XS_ERR_ARG, "xs_gpu_init: SimulationData has NULL material arrays");
+    // All three big arrays NULL = build the problem on the device (xs_generate.cuh).
+    const bool generate = !sd->nuclide_grid && !sd->unionized_energy_array && !sd->index_grid;
+    if (!generate) {
+        if (!sd->nuclide_grid) return set_error(XS_ERR_ARG, "xs_gpu_init: nuclide_grid is NULL");
+        if (sd->length_nuclide_grid != in->n_isotopes * in->n_gridpoints)
+            return set_error(XS_ERR_ARG, "xs_gpu_init: length_nuclide_grid does not match Inputs");
+        if (in->grid_type == XS_UNIONIZED &&
+            (!sd->unionized_energy_array || !sd->index_grid ||
+             sd->length_index_grid != (long)sd->length_unionized_energy_array * in->n_isotopes))
+            return set_error(XS_ERR_ARG, "xs_gpu_init: unionized grid arrays missing or inconsistent");
+        if (in->grid_type == XS_HASH &&
+            (!sd->index_grid || in->hash_bins < 1 || sd->length_index_grid != (long)in->hash_bins * in->n_isotopes))
+            return set_error(XS_ERR_ARG, "xs_gpu_init: hash grid missing or inconsistent");
+    } else if (in->grid_type == XS_HASH && in->hash_bins < 1) {
+        return set_error(XS_ERR_ARG, "xs_gpu_init: hash_bins must be >= 1");
+    }
 
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -769,7 +792,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->n_gp = in->n_gridpoints;
     ctx->hash_bins = in->hash_bins;
     ctx->max_num_nucs = sd->max_num_nucs;
-    ctx->n_ueg = in->grid_type == XS_UNIONIZED ? sd->length_unionized_energy_array : 0;
+    ctx->n_ueg = in->grid_type == XS_UNIONIZED ? in->n_isotopes * in->n_gridpoints : 0;
     ctx->gather = env_int("XSB200_GATHER", xs::kTriple) ? xs::kTriple : xs::kLanePerNuclide;
     ctx->blocks_per_sm = env_int("XSB200_BLOCKS_PER_SM", 0);
     ctx->sweep = env_int("XSB200_SWEEP", 1);
@@ -969,6 +992,27 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
         return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
     CUDA_TRY(cudaMemcpyAsync(h_perm_out, sorted_perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
+    return XS_OK;
+}
+
+int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_bytes, void *h_dst)
+{
+    if (!ctx || !h_dst || offset_bytes < 0 || n_bytes < 0) return set_error(XS_ERR_ARG, "xs_gpu_read_array: bad argument");
+    DeviceState &d = ctx->dev[0];
+    const long n_points = ctx->n_iso * ctx->n_gp;
+    const unsigned char *src = nullptr;
+    long total = 0;
+    if (which == XS_ARRAY_NUCLIDE_GRID) { src = reinterpret_cast<const unsigned char *>(d.grid); total = n_points * 48; }
+    else if (which == XS_ARRAY_UNIONIZED_ENERGY && ctx->grid_type == XS_UNIONIZED) {
+        src = reinterpret_cast<const unsigned char *>(d.P.ueg); total = n_points * 8;
+    } else if (which == XS_ARRAY_INDEX_GRID && ctx->grid_type != XS_NUCLIDE) {
+        src = reinterpret_cast<const unsigned char *>(d.P.index_grid);
+        total = (ctx->grid_type == XS_UNIONIZED ? n_points : (long)ctx->hash_bins) * ctx->n_iso * 4;
+    } else return set_error(XS_ERR_ARG, "xs_gpu_read_array: array %d does not exist for this grid type", which);
+    if (offset_bytes + n_bytes > total) return set_error(XS_ERR_ARG, "xs_gpu_read_array: range beyond the array (%ld bytes)", total);
+    CUDA_TRY(cudaSetDevice(d.device));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    CUDA_TRY(cudaMemcpy(h_dst, src + offset_bytes, (size_t)n_bytes, cudaMemcpyDeviceToHost));
     return XS_OK;
 }
 

@@ -50,14 +50,16 @@ inline void sort_scratch_free(SortScratch &s)
     s.tile_hist = nullptr; s.chunk_sum = nullptr; s.n_tiles_capacity = 0;
 }
 
-XS_DEV uint32_t sort_digit(uint32_t key, int shift, uint32_t mask, int nonzero_flag)
+template <typename KeyT>
+XS_DEV uint32_t sort_digit(KeyT key, int shift, uint32_t mask, int nonzero_flag)
 {
-    const uint32_t d = (key >> shift) & mask;
+    const uint32_t d = (uint32_t)(key >> shift) & mask;
     return nonzero_flag ? (uint32_t)(d != 0) : d;
 }
 
+template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-sort_hist_kernel(const uint32_t *__restrict__ keys, long n, int shift, uint32_t mask, int nonzero_flag,
+sort_hist_kernel(const KeyT *__restrict__ keys, long n, int shift, uint32_t mask, int nonzero_flag,
                  unsigned int *__restrict__ tile_hist, int n_tiles)
 {
     __shared__ unsigned int h[kRadix];
@@ -137,9 +139,10 @@ sort_scan_kernel(unsigned int *data, long total, const unsigned int *chunk_sum)
     for (int i = 0; i < 4; i++) if (base + i < total) { data[base + i] = run; run += v[i]; }
 }
 
+template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, long n, int shift,
+sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                    KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, long n, int shift,
                     uint32_t mask, int nonzero_flag, const unsigned int *__restrict__ tile_base, int n_tiles)
 {
     __shared__ unsigned int warp_cnt[kSortWarps][kRadix];
@@ -149,14 +152,14 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const long base = (long)blockIdx.x * kSortTile + (long)warp * (32 * kSortItems);
-    uint32_t key[kSortItems];
+    KeyT key[kSortItems];
     unsigned short rank[kSortItems];
 
 #pragma unroll
     for (int r = 0; r < kSortItems; r++) {
         const long idx = base + r * 32 + lane;
         const bool valid = idx < n;
-        key[r] = valid ? keys_in[idx] : 0u;
+        key[r] = valid ? keys_in[idx] : (KeyT)0;
         const uint32_t d = valid ? sort_digit(key[r], shift, mask, nonzero_flag) : (uint32_t)kRadix;
         const unsigned peers = __match_any_sync(kFullMask, d);
         const int leader = __ffs(peers) - 1;
@@ -193,34 +196,46 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
     }
 }
 
-// Sort bits [lo_bit, hi_bit) of key[0][0..n).  key[]/perm[] are ping-pong buffers; on return
-// *sorted_perm points at the buffer holding the final permutation.  Returns 0 on success.
-inline int sort_lookups(SortScratch &s, uint32_t *key[2], uint32_t *perm[2], long n, int lo_bit, int hi_bit,
-                        int nonzero_flag, cudaStream_t stream, uint32_t **sorted_perm, int *launches)
+// Sort bits [lo_bit, hi_bit) of key[0][0..n), 8 bits per pass, stable.  key[]/perm[] are
+// ping-pong buffers; the payload starts as the identity unless `payload_ready` says perm[0]
+// already holds one.  On return *sorted_perm / *sorted_key point at the buffers holding the
+// final payload and keys.  Returns 0 on success.
+template <typename KeyT>
+inline int radix_sort(SortScratch &s, KeyT *key[2], uint32_t *perm[2], long n, int lo_bit, int hi_bit,
+                      int nonzero_flag, bool payload_ready, cudaStream_t stream, uint32_t **sorted_perm,
+                      KeyT **sorted_key, int *launches)
 {
     const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
-    if (n_tiles == 0) { *sorted_perm = perm[0]; return 0; }
+    if (n_tiles == 0) { *sorted_perm = perm[0]; if (sorted_key) *sorted_key = key[0]; return 0; }
     if (n_tiles > s.n_tiles_capacity) return -1;
     int cur = 0;
-    bool first = true;
+    bool first = !payload_ready;
     for (int shift = lo_bit; shift < hi_bit; shift += 8) {
         const int bits = std::min(8, hi_bit - shift);
         const uint32_t mask = (1u << bits) - 1u;
-        sort_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(key[cur], n, shift, mask, nonzero_flag, s.tile_hist, n_tiles);
+        sort_hist_kernel<KeyT><<<n_tiles, kSortThreads, 0, stream>>>(key[cur], n, shift, mask, nonzero_flag, s.tile_hist, n_tiles);
         const long n_counters = (long)n_tiles * kRadix;
         const int n_chunks = (int)((n_counters + kScanChunk - 1) / kScanChunk);
         sort_chunk_sum_kernel<<<n_chunks, kScanThreads, 0, stream>>>(s.tile_hist, n_counters, s.chunk_sum);
         sort_scan_kernel<<<n_chunks, kScanThreads, 0, stream>>>(s.tile_hist, n_counters, s.chunk_sum);
-        sort_scatter_kernel<<<n_tiles, kSortThreads, 0, stream>>>(key[cur], first ? nullptr : perm[cur], key[cur ^ 1],
-                                                                  perm[cur ^ 1], n, shift, mask, nonzero_flag,
-                                                                  s.tile_hist, n_tiles);
+        sort_scatter_kernel<KeyT><<<n_tiles, kSortThreads, 0, stream>>>(key[cur], first ? nullptr : perm[cur], key[cur ^ 1],
+                                                                        perm[cur ^ 1], n, shift, mask, nonzero_flag,
+                                                                        s.tile_hist, n_tiles);
         if (cudaGetLastError() != cudaSuccess) return -1;
-        *launches += 4;
+        if (launches) *launches += 4;
         cur ^= 1;
         first = false;
     }
     *sorted_perm = perm[cur];
+    if (sorted_key) *sorted_key = key[cur];
     return 0;
+}
+
+// The lookup sort of -k 6 / xs_gpu_sort_keys: 32-bit keys, identity payload.
+inline int sort_lookups(SortScratch &s, uint32_t *key[2], uint32_t *perm[2], long n, int lo_bit, int hi_bit,
+                        int nonzero_flag, cudaStream_t stream, uint32_t **sorted_perm, int *launches)
+{
+    return radix_sort<uint32_t>(s, key, perm, n, lo_bit, hi_bit, nonzero_flag, false, stream, sorted_perm, nullptr, launches);
 }
 
 }  // namespace xs

@@ -71,6 +71,11 @@ def grid_init_do_not_profile(inp: Inputs, mype: int = 1) -> SimulationData:
     return _abi.host_lib().grid_init_do_not_profile(inp, mype)
 
 
+def materials_only(inp: Inputs) -> SimulationData:
+    """Material tables only; passing this to move_simulation_data_to_device builds the grids on the GPU."""
+    return _abi.host_lib().xs_materials_only(inp)
+
+
 def free_simulation_data(sd: SimulationData) -> None:
     _abi.host_lib().xs_free_simulation_data(C.byref(sd))
 
@@ -177,6 +182,17 @@ class DeviceSimulation:
         self._check(self._lib.xs_gpu_sort_keys(self._ctx, keys.ctypes.data, keys.shape[0], lo_bit, hi_bit, perm.ctypes.data))
         return perm
 
+    def read_array(self, which: str) -> np.ndarray:
+        """Download one device-resident problem array: 'nuclide_grid' (f64, 6 per point),
+        'unionized_energy_array' (f64) or 'index_grid' (i32)."""
+        info = self.info()
+        pts = info.n_isotopes * info.n_gridpoints
+        code, dtype, n = {"nuclide_grid": (0, np.float64, pts * 6), "unionized_energy_array": (1, np.float64, pts),
+                          "index_grid": (2, np.int32, (pts if info.grid_type == UNIONIZED else info.hash_bins) * info.n_isotopes)}[which]
+        out = np.empty(n, dtype=dtype)
+        self._check(self._lib.xs_gpu_read_array(self._ctx, code, 0, out.nbytes, out.ctypes.data))
+        return out
+
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self._lib.xs_gpu_set_stream(self._ctx, cuda_stream))
 
@@ -215,5 +231,5 @@ def expected_checksum(inp: Inputs) -> Optional[int]:
 __all__ = [
     "CLIError", "DeviceSimulation", "EVENT_BASED", "HASH", "HISTORY_BASED", "NUCLIDE", "RunResult",
     "UNIONIZED", "XSGpuError", "expected_checksum", "free_simulation_data", "grid_init_do_not_profile",
-    "make_inputs", "move_simulation_data_to_device", "read_CLI", "simulation_arrays",
+    "make_inputs", "materials_only", "move_simulation_data_to_device", "read_CLI", "simulation_arrays",
 ]

@@ -142,6 +142,7 @@ void print_CLI_error(void)
           "  --reps <n>               Timed repetitions after one warm-up (default 1, no warm-up)\n"
           "  --json                   Also print one machine-readable JSON line\n"
           "  --dump-xs <n>            Print energy, material and macro_xs of the first n lookups\n"
+          "  --device-init            Build the synthetic problem on the GPU instead of the host\n"
           "Default is equivalent to: -m history -s large -l 34 -p 500000 -G unionized -k 0\n"
           "See readme for full description of default run values\n", stdout);
     exit(4);
@@ -159,12 +160,13 @@ Inputs read_CLI(int argc, char *argv[])
 /* Removes this driver's long options from argv (the reference would reject them). */
 int xs_strip_driver_opts(int *argc, char *argv[], xs_driver_opts *o)
 {
-    o->gpus = 1; o->reps = 1; o->json = 0; o->dump_xs = 0;
+    o->gpus = 1; o->reps = 1; o->json = 0; o->dump_xs = 0; o->device_init = 0;
     int w = 1;
     for (int r = 1; r < *argc; r++) {
         const char *a = argv[r];
         int has_val = r + 1 < *argc;
         if (strcmp(a, "--json") == 0)                     o->json = 1;
+        else if (strcmp(a, "--device-init") == 0)         o->device_init = 1;
         else if (strcmp(a, "--gpus") == 0 && has_val)     o->gpus = atoi(argv[++r]);
         else if (strcmp(a, "--reps") == 0 && has_val)     o->reps = atoi(argv[++r]);
         else if (strcmp(a, "--dump-xs") == 0 && has_val)  o->dump_xs = atol(argv[++r]);

@@ -261,6 +261,19 @@ SimulationData grid_init_do_not_profile(Inputs in, int mype)
     return sd;
 }
 
+SimulationData xs_materials_only(Inputs in)
+{
+    SimulationData sd;
+    memset(&sd, 0, sizeof sd);
+    sd.num_nucs = load_num_nucs(in.n_isotopes);
+    sd.length_num_nucs = XS_NUM_MATERIALS;
+    sd.mats = load_mats(sd.num_nucs, in.n_isotopes, &sd.max_num_nucs);
+    sd.length_mats = sd.length_num_nucs * sd.max_num_nucs;
+    sd.concs = load_concs(sd.num_nucs, sd.max_num_nucs);
+    sd.length_concs = sd.length_mats;
+    return sd;
+}
+
 void xs_free_simulation_data(SimulationData *sd)
 {
     free(sd->num_nucs); free(sd->concs); free(sd->mats);

@@ -33,9 +33,13 @@ int main(int argc, char *argv[])
 
     print_inputs(in, opt.gpus, XS_VERSION);
 
-    SimulationData SD = (in.binary_mode == XS_BINARY_READ) ? binary_read(in)
-                                                           : grid_init_do_not_profile(in, mype);
-    if (in.binary_mode == XS_BINARY_WRITE)
+    SimulationData SD;
+    if (in.binary_mode == XS_BINARY_READ) SD = binary_read(in);
+    else if (opt.device_init) {
+        printf("Building nuclide grids and acceleration structure on the GPU...\n");
+        SD = xs_materials_only(in);
+    } else SD = grid_init_do_not_profile(in, mype);
+    if (in.binary_mode == XS_BINARY_WRITE && !opt.device_init)
         binary_write(in, SD);
 
     printf("Allocating and moving simulation data to GPU memory space...\n");

@@ -42,13 +42,16 @@ int    xs_parse_cli(int argc, char *argv[], Inputs *out, char *err, size_t errle
 /* Reference-compatible wrapper: prints usage and exit(4) on error (cuda/io.cu:208-224). */
 Inputs read_CLI(int argc, char *argv[]);
 void   print_CLI_error(void);
-/* Extra long options of this driver (--gpus N, --reps N, --json, --dump-xs N), stripped
+/* Extra long options of this driver (--gpus N, --reps N, --json, --dump-xs N, --device-init), stripped
  * from argv before read_CLI sees it. */
-typedef struct { int gpus; int reps; int json; long dump_xs; } xs_driver_opts;
+typedef struct { int gpus; int reps; int json; long dump_xs; int device_init; } xs_driver_opts;
 int    xs_strip_driver_opts(int *argc, char *argv[], xs_driver_opts *o);
 
 /* ---- data generation --------------------------------------------------------------- */
 SimulationData grid_init_do_not_profile(Inputs in, int mype);
+/* Only the material tables (num_nucs, mats, concs); the three big arrays stay NULL, which asks
+ * xs_gpu_init to build them on the device. */
+SimulationData xs_materials_only(Inputs in);
 void   xs_free_simulation_data(SimulationData *sd);
 int   *load_num_nucs(long n_isotopes);
 int   *load_mats(int *num_nucs, long n_isotopes, int *max_num_nucs);
