@@ -1,4 +1,7 @@
 #!/bin/bash
-python -m pytest tests -m "gpu and not slow" -x -q 2>&1 | tail -5
-python -m pytest tests -m "gpu" -x -q -k "official_large" 2>&1 | tail -3
-xsbench_b200/xsbench -m event -s large -k 4 --device-init --reps 3 2>&1 | grep -E "Building|Allocated|Device time|Lookups/s|checksum"
+S=$(date +%s.%N)
+xsbench_b200/xsbench -m event -s XL -k 6 --device-init --reps 3 2>&1 | grep -E "Building|Allocated|Device time|Phases|Lookups/s|checksum|failed"
+E=$(date +%s.%N); echo "wall: $(echo "$E - $S" | bc) s"
+S=$(date +%s.%N)
+xsbench_b200/xsbench -m event -s XL -l 1000000 -k 4 --device-init 2>&1 | grep -E "checksum|failed"
+E=$(date +%s.%N); echo "wall: $(echo "$E - $S" | bc) s"
