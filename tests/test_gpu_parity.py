@@ -328,6 +328,27 @@ def test_xl_problem_golden_checksum():
 
 
 @pytest.mark.slow
+def test_xxl_hash_grid_golden_checksum():
+    """-s XXL (355 x 501,578 points, 8 GB nuclide grid) with -G hash, generated on the device:
+    golden 344 for -l 1000000 from the reference.  XXL *unionized* (245 GiB) does not
+    fit one B200 and is reported as out of memory, not silently degraded."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100 * 2**30:
+        pytest.skip("needs a large GPU")
+    inp = xs.make_inputs(size="XXL", method="event", grid="hash", lookups=1000000, kernel_id=4)
+    assert inp.n_gridpoints == 501578
+    mats = xs.materials_only(inp)
+    with xs.move_simulation_data_to_device(inp, mats) as gpu:
+        assert gpu.run().checksum == 344
+        assert gpu.run(xs.make_inputs(size="XXL", method="event", grid="hash", lookups=1000000, kernel_id=0)).checksum == 344
+    big = xs.make_inputs(size="XXL", method="event", grid="unionized", lookups=1000)
+    with pytest.raises(xs.XSGpuError) as ei:
+        xs.move_simulation_data_to_device(big, mats)
+    assert ei.value.code == _abi.XS_ERR_CUDA
+    xs.free_simulation_data(mats)
+
+
+@pytest.mark.slow
 def test_official_large_event_full_size():
     """The canonical FOM configuration (BASELINE.json configs[1]): 355 nuclides, 5.6 GB."""
     inp = xs.make_inputs(size="large", method="event")

@@ -1,19 +1,21 @@
 // xs_kernels.cuh -- the lookup kernels.
 //
-// One kernel body serves every event-mode variant (-k 0..6) and the host-sample entry
-// point; what changes between variants is where a warp's batch of 32 lookups comes from
-// (sampled in-kernel from the lookup id, or read from sample arrays, optionally through a
-// permutation / material filter) -- see xs_gpu.cu for the dispatch.
+// Two families (dispatch in xs_gpu.cu):
 //
-// Work decomposition (B200: 148 SMs x 64 resident warps):
-//   * persistent grid, warps fetch BATCHES of 32 lookups from a global atomic counter;
-//   * inside a batch the per-lookup scalar work is lane-parallel: lane l draws the sample of
-//     lookup l (LCG skip-ahead) and finds its unionized-grid row / hash bin;
-//   * the gather is warp-cooperative: the warp walks the batch one lookup at a time and
-//     spreads that lookup's nuclides over its lanes (two lane mappings, see Gather below);
-//   * per-channel sums are combined with warp shuffles; lane l keeps lookup l's argmax;
-//   * the verification sum is reduced warp -> block -> one atomicAdd(u64) per block, so the
-//     reference's 136 MB verification[] array and its thrust::reduce pass do not exist.
+//  * SWEEP pipeline (-k 4/5/6, xs_gpu_lookup_samples, history mode) -- the fast path:
+//      xs_sample_kernel / xs_locate_kernel / xs_history_step_kernel   energy, material, UEG row, histogram
+//      xs_partition_kernel (or radix sort + xs_gather_kernel)         group the lookups by material
+//      xs_window_kernel                                               per material and nuclide window:
+//                                                                     pair records from L2, 4 lanes per lookup
+//  * IN-ORDER kernel (-k 0..3, xs_gpu_dump): xs_event_kernel -- one kernel body; what changes
+//    between variants is where a warp's batch of 32 lookups comes from (sampled in-kernel
+//    from the lookup id, or read from sample arrays, optionally through a material filter).
+//      - persistent grid, warps fetch BATCHES of 32 lookups from a global atomic counter;
+//      - lane-parallel scalar work: lane l draws the sample of lookup l and finds its row/bin;
+//      - small materials one lookup per lane in reference order (lane_macro_small), fuel by the
+//        whole warp, 3 lanes per nuclide (warp_macro_big), shuffle reduction, near-tie guard;
+//      - verification sum reduced warp -> block -> one atomicAdd(u64) per block, so the
+//        reference's 136 MB verification[] array and its thrust::reduce pass do not exist.
 #pragma once
 
 #include "xs_device.cuh"
@@ -25,10 +27,10 @@ constexpr int kWarpsPerBlock = kBlockThreads / 32;
 constexpr double kTieGuard = 1e-10;      // relative gap below which order of summation could
                                          // change an integer decision -> settle serially
 
-// Gather strategies.
-//   kLanePerNuclide : every lookup by the whole warp, lane j handles nuclide j (+32, ...):
+// Gather strategies of the in-order kernel (XSB200_GATHER).
+//   kLanePerNuclide (0): every lookup by the whole warp, lane j handles nuclide j (+32, ...):
 //                     6 divergent 16-B loads per lane and round.  Simple; kept for comparison.
-//   kTriple (default, "hybrid"): small materials (n <= 32) are evaluated one lookup per lane
+//   kTriple (1, default, "hybrid"): small materials (n <= 32) are evaluated one lookup per lane
 //                     (phase A, lane_macro_small); big ones (fuel) by the whole warp with 3
 //                     lanes per nuclide and kBigUnroll x 10 nuclides in flight (phase B,
 //                     warp_macro_big).
