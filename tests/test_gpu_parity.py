@@ -94,6 +94,12 @@ def test_run_range_partition_is_exact(small):
     assert far.verification == small.oracle.event(900_000_000, 1000, NTHREADS)
     empty = small.gpu.run_range(5, 0)
     assert empty.verification == 0 and empty.n_lookups == 0
+    for k in (1, 4, 6):
+        grid = {0: "unionized", 1: "nuclide", 2: "hash"}[small.inp.grid_type]
+        inp_k = xs.make_inputs(size="small", grid=grid, gridpoints=1000, hash_bins=500, method="event", lookups=10, kernel_id=k)
+        assert small.gpu.run_range(7, 0, inp_k).n_lookups == 0
+        one = small.gpu.run_range(7, 1, inp_k)
+        assert one.n_lookups == 1 and one.verification == small.oracle.event(7, 1, 1)
 
 
 # ---- host-sample entry point (edge cases) ----------------------------------------------------------

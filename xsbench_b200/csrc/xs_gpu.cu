@@ -103,6 +103,9 @@ struct DeviceState {
     cudaStream_t copy_stream = nullptr;    // host->device copies of a host-sample call overlap its compute
     cudaEvent_t ev_copy[kMaxChunks] = {}, ev_ready = nullptr;
     int launches = 0;
+    // a grouped batch whose histogram read-back has been enqueued but not yet consumed
+    struct Pending { bool active = false; int kernel_id = 0; long base = 0, count = 0; const uint32_t *id = nullptr;
+                     xs::BatchSink sink{}; } pending;
 };
 
 }  // namespace
@@ -507,24 +510,23 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
 // histogram and, for -k 6, key[0] are ready in device memory): regroup, then sweep material by
 // material.  `base` offsets every per-sample buffer (chunks of a host-sample call); `hist` /
 // `cursor` are this batch's device counters.
-int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long base, long count,
-                           unsigned int *hist, unsigned int *cursor, xs::BatchSink sink, bool record_event)
+// Front half: regroup (radix sort or one-pass partition) and start the 64-byte histogram
+// read-back.  Nothing here waits for the device, so several GPUs can be fed back to back.
+int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long base, long count,
+                          unsigned int *hist, unsigned int *cursor, xs::BatchSink sink, bool record_event)
 {
-    int rc = XS_OK;
-    GroupedBatch b{};
-    b.energy = d.grp_e + base;
-    b.where = d.grp_where + base;
-    b.partial = d.sweep_partial + 3 * base;
+    CUDA_TRY(cudaSetDevice(d.device));
+    const uint32_t *id = nullptr;
     if (kernel_id == 6) {
         // optimization 6 (cuda/Simulation.cu:1024-1099): sort by (material, energy)
         uint32_t *sorted_perm = nullptr;
-        rc = xs::sort_lookups(d.sort, d.key, d.perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
+        int rc = xs::sort_lookups(d.sort, d.key, d.perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
         if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
         const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
         xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e, d.samp_where, count, d.grp_e, d.grp_where);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
-        b.id = sorted_perm;
+        id = sorted_perm;
     } else {
         // optimization 4 (:754-821): group by material; optimization 5 (:895-958): fuel first
         const int tiles = (int)((count + 256 * xs::kPartItems - 1) / (256 * xs::kPartItems));
@@ -533,20 +535,44 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
                                                            kernel_id == 5 ? d.grp_mat + base : nullptr, d.grp_id + base);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
-        b.id = d.grp_id + base;
+        id = d.grp_id + base;
     }
     if (record_event) CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
     // group sizes: the sampler's histogram (64 bytes device -> pinned host; the window launches
-    // below take slot ranges as kernel arguments, which measured 5 % faster than deriving them
-    // on the device)
+    // take slot ranges as kernel arguments, which measured 5 % faster than deriving them on
+    // the device)
     CUDA_TRY(cudaMemcpyAsync(d.h_hist, hist, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, d.stream));
+    d.pending.active = true;
+    d.pending.kernel_id = kernel_id;
+    d.pending.base = base;
+    d.pending.count = count;
+    d.pending.id = id;
+    d.pending.sink = sink;
+    return XS_OK;
+}
+
+// Back half: wait for the histogram, then sweep material by material.
+int enqueue_grouped_back(xs_gpu_ctx *ctx, DeviceState &d)
+{
+    if (!d.pending.active) return XS_OK;
+    d.pending.active = false;
+    const int kernel_id = d.pending.kernel_id;
+    const long base = d.pending.base, count = d.pending.count;
+    const xs::BatchSink sink = d.pending.sink;
+    CUDA_TRY(cudaSetDevice(d.device));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
+    GroupedBatch b{};
+    b.energy = d.grp_e + base;
+    b.where = d.grp_where + base;
+    b.partial = d.sweep_partial + 3 * base;
+    b.id = d.pending.id;
     long offset = 0;
     for (int m = 0; m < XS_NUM_MATERIALS; m++) {
         b.offset[m] = offset;
         b.count[m] = d.h_hist[m];
         offset += d.h_hist[m];
     }
+    int rc = XS_OK;
     if (kernel_id == 5) {
         // fuel -> windowed sweep; the other 11 materials stay mixed -> one in-order launch
         const int fuel = 0;
@@ -567,6 +593,17 @@ int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long 
     return launch_sweep(ctx, d, b, XS_NUM_MATERIALS, mats, sink);
 }
 
+// Sorted variants on device-resident samples (samp_e / samp_mat / samp_where, the material
+// histogram and, for -k 6, key[0] are ready in device memory): regroup, then sweep material by
+// material.  `base` offsets every per-sample buffer (chunks of a host-sample call); `hist` /
+// `cursor` are this batch's device counters.
+int enqueue_grouped_lookup(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long base, long count,
+                           unsigned int *hist, unsigned int *cursor, xs::BatchSink sink, bool record_event)
+{
+    int rc = enqueue_grouped_front(ctx, d, kernel_id, base, count, hist, cursor, sink, record_event);
+    return rc == XS_OK ? enqueue_grouped_back(ctx, d) : rc;
+}
+
 // One device's share of an event-mode run: ids [first_id, first_id + count).
 int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count, bool first_pass);
 
@@ -574,27 +611,59 @@ int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long firs
 // `max_pass` lookups, so the sample / grouping buffers stay bounded (112 B per lookup) however
 // many lookups are requested (BASELINE config 5: 1e9+ lookups).  The verification sum simply
 // accumulates over the passes.
-int enqueue_event(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count)
+int enqueue_event_all(xs_gpu_ctx *ctx, int kernel_id, long first_id, long count)
 {
-    CUDA_TRY(cudaSetDevice(d.device));
-    d.launches = 0;
-    CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
-    const long max_pass = kernel_id == 0 ? count : ctx->max_pass;
-    int rc = XS_OK;
-    long done = 0;
-    do {
-        const long n = std::min(count - done, std::max<long>(max_pass, 1));
-        rc = enqueue_event_pass(ctx, d, kernel_id, first_id + done, n, done == 0);
-        done += n;
-    } while (rc == XS_OK && done < count);
-    if (rc != XS_OK) return rc;
-    CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
+    const int n = (int)ctx->dev.size();
+    long lo[8], cnt[8], done[8];
+    long most = 0;
+    for (int g = 0; g < n; g++) {
+        DeviceState &d = ctx->dev[g];
+        lo[g] = first_id + count * g / n;
+        cnt[g] = first_id + count * (g + 1) / n - lo[g];
+        done[g] = 0;
+        most = std::max(most, cnt[g]);
+        CUDA_TRY(cudaSetDevice(d.device));
+        d.launches = 0;
+        CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    }
+    const long max_pass = kernel_id == 0 ? std::max<long>(most, 1) : std::max<long>(ctx->max_pass, 1);
+    bool more = true, first = true;
+    while (more) {
+        more = false;
+        // front halves on every GPU first (nothing waits), then the back halves: the GPUs of
+        // one process start their sweeps together instead of one histogram read-back apart
+        for (int g = 0; g < n; g++) {
+            const long todo = std::min(cnt[g] - done[g], max_pass);
+            if (todo <= 0 && !(first && cnt[g] == 0)) continue;
+            CUDA_TRY(cudaSetDevice(ctx->dev[g].device));
+            int rc = enqueue_event_pass(ctx, ctx->dev[g], kernel_id, lo[g] + done[g], std::max<long>(todo, 0), first);
+            if (rc != XS_OK) return rc;
+            done[g] += std::max<long>(todo, 0);
+            more |= done[g] < cnt[g];
+        }
+        for (int g = 0; g < n; g++) {
+            int rc = enqueue_grouped_back(ctx, ctx->dev[g]);
+            if (rc != XS_OK) return rc;
+        }
+        first = false;
+    }
+    for (int g = 0; g < n; g++) {
+        CUDA_TRY(cudaSetDevice(ctx->dev[g].device));
+        CUDA_TRY(cudaEventRecord(ctx->dev[g].ev[EV_LOOKED_UP], ctx->dev[g].stream));
+    }
     return XS_OK;
 }
 
 int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long first_id, long count, bool first_pass)
 {
+    if (count <= 0) {                      // an empty share still needs its phase marks
+        if (first_pass) {
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+        }
+        return XS_OK;
+    }
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
 
@@ -640,7 +709,7 @@ int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long firs
                 if (rc == XS_OK) rc = launch_event(ctx, d, src, sink, 1);
             }
         } else {
-            rc = enqueue_grouped_lookup(ctx, d, kernel_id, 0, count, d.histogram, d.counters + kCursorBase, sink, first_pass);
+            rc = enqueue_grouped_front(ctx, d, kernel_id, 0, count, d.histogram, d.counters + kCursorBase, sink, first_pass);
         }
     }
     return rc;
@@ -855,11 +924,15 @@ int xs_gpu_run_range(xs_gpu_ctx *ctx, const Inputs *in, long first_id, long coun
 
     const double t0 = wall_seconds();
     const int n = (int)ctx->dev.size();
-    for (int g = 0; g < n; g++) {
-        const long lo = first_id + count * g / n, hi = first_id + count * (g + 1) / n;
-        int rc = event ? enqueue_event(ctx, ctx->dev[g], in->kernel_id, lo, hi - lo)
-                       : enqueue_history(ctx, ctx->dev[g], lo, hi - lo, in->lookups);
+    if (event) {
+        int rc = enqueue_event_all(ctx, in->kernel_id, first_id, count);
         if (rc != XS_OK) return rc;
+    } else {
+        for (int g = 0; g < n; g++) {
+            const long lo = first_id + count * g / n, hi = first_id + count * (g + 1) / n;
+            int rc = enqueue_history(ctx, ctx->dev[g], lo, hi - lo, in->lookups);
+            if (rc != XS_OK) return rc;
+        }
     }
     return finish_run(ctx, res, t0);
 }
