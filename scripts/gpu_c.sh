@@ -1,7 +1,4 @@
 #!/bin/bash
-S=$(date +%s.%N)
-xsbench_b200/xsbench -m event -s XL -k 6 --device-init --reps 3 2>&1 | grep -E "Building|Allocated|Device time|Phases|Lookups/s|checksum|failed"
-E=$(date +%s.%N); echo "wall: $(echo "$E - $S" | bc) s"
-S=$(date +%s.%N)
-xsbench_b200/xsbench -m event -s XL -l 1000000 -k 4 --device-init 2>&1 | grep -E "checksum|failed"
-E=$(date +%s.%N); echo "wall: $(echo "$E - $S" | bc) s"
+python -m pytest tests -m "gpu and not slow" -x -q 2>&1 | tail -3
+python scripts/quick_bench.py --grid nuclide --kernels 0,4,6 XSB200_NUCLIDE_BUCKETS=1 XSB200_NUCLIDE_BUCKETS=0 2>&1 | tail -6
+python scripts/quick_bench.py --grid nuclide --method history --kernels 0 2>&1 | tail -1

@@ -38,12 +38,15 @@ struct Problem {
     const double2 *pairs;        // pair records (see xs_build_pairs_kernel): 8 chunks = 128 B per
                                  //   (nuclide, k): low point k and high point k+1 interleaved
     const uint32_t *ueg_bucket;  // [n_buckets+1]      bucket -> first UEG row in it
+    const uint32_t *nuc_bucket;  // [n_iso][nuc_buckets+1]  per-nuclide bucket -> first grid point in it
+                                 //   (nuclide-grid mode only; replaces the top of grid_search_nuclide)
     const int     *mat_first;    // [13]  CSR offsets of the compact material table
     const int     *mat_nuc;      // [mat_first[12]]    nuclide id
     const double  *mat_conc;     // [mat_first[12]]    concentration
     long   n_ueg;
     double bucket_scale;         // (double)n_buckets
     int    n_buckets;
+    int    nuc_buckets;          // buckets per nuclide (0 = table not built)
     int    n_iso;
     int    n_gp;
     int    hash_bins;
@@ -259,7 +262,22 @@ XS_DEV int nuclide_low(const Problem &P, double e, long where, int nuc)
     if (GRID == kUnionized) {
         low = ldg_index_stream(P.index_grid + where * P.n_iso + nuc);
     } else if (GRID == kNuclide) {
-        low = REC ? search_nuclide_rec(P, base, e, 0, last) : search_nuclide(g, e, 0, last);
+        if (P.nuc_buckets > 0) {
+            // upper_bound(e) lies in [bucket[b], bucket[b+1]] (same argument as for the UEG table);
+            // grid_search_nuclide(0, last) = clamp(upper_bound - 1, 0, last - 1)
+            const int b = bucket_of(e, (double)P.nuc_buckets, P.nuc_buckets);
+            const uint32_t *t = P.nuc_bucket + (long)nuc * (P.nuc_buckets + 1) + b;
+            int lo = (int)__ldg(t), hi = (int)__ldg(t + 1);
+            while (hi - lo > 4) {
+                const int mid = lo + (hi - lo) / 2;
+                if (ldg_grid_energy(g + 3 * (long)mid) > e) hi = mid; else lo = mid + 1;
+            }
+            while (lo < hi && !(ldg_grid_energy(g + 3 * (long)lo) > e)) lo++;
+            low = lo - 1;
+            if (low < 0) low = 0;
+        } else {
+            low = REC ? search_nuclide_rec(P, base, e, 0, last) : search_nuclide(g, e, 0, last);
+        }
     } else {
         const int u_lo = ldg_index_keep(P.index_grid + where * P.n_iso + nuc);
         const int u_hi = (where == P.hash_bins - 1)

@@ -89,6 +89,7 @@ struct DeviceState {
     uint32_t *key[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     xs::SortScratch sort{};
     double2 *pairs = nullptr;              // pair records for the window kernel (128 B per grid point)
+    uint32_t *nuc_bucket = nullptr;        // nuclide-grid mode: per-nuclide search tables
     uint32_t *samp_where = nullptr;        // [sample_capacity] UEG row / hash bin per sample
     double *grp_e = nullptr;               // samples grouped by material: energy,
     uint32_t *grp_where = nullptr;         //   row / bin,
@@ -263,6 +264,19 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     if (ctx->grid_type == XS_UNIONIZED) {
         xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(ueg, n_points, (double)n_buckets, (int)n_buckets, bucket);
         CUDA_TRY(cudaGetLastError());
+    }
+    if (ctx->grid_type == XS_NUCLIDE && env_int("XSB200_NUCLIDE_BUCKETS", 1)) {
+        // nuclide-grid mode: a bucket table per nuclide replaces the top ~12 of the 14 (large)
+        // dependent probes of grid_search_nuclide; ~2 grid points per bucket
+        long nb = 1;
+        while (nb * 2 <= n_gp / 2 && nb < 65536) nb *= 2;
+        const size_t nb_bytes = (size_t)n_iso * (size_t)(nb + 1) * sizeof(uint32_t);
+        CUDA_TRY(cudaMalloc(&d.nuc_bucket, nb_bytes));
+        xs::xs_build_nuclide_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, (int)nb, d.nuc_bucket);
+        CUDA_TRY(cudaGetLastError());
+        d.resident_bytes += nb_bytes;
+        P.nuc_bucket = d.nuc_bucket;
+        P.nuc_buckets = (int)nb;
     }
     // pair records (B200 layout for the windowed sweep): one 128-byte line per (nuclide, k)
     const size_t pair_bytes = (size_t)n_points * 8 * sizeof(double2);
@@ -1133,7 +1147,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         xs::sort_scratch_free(d.sort);
         cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
-        cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd);
+        cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd); cudaFree(d.nuc_bucket);
         cudaFree(d.dump_macro);
         if (d.h_accum) cudaFreeHost(d.h_accum);
         if (d.h_hist) cudaFreeHost(d.h_hist);

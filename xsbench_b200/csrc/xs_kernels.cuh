@@ -658,6 +658,22 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     }
 }
 
+// Per-nuclide bucket tables for nuclide-grid mode (init only): bucket[i][b] = number of grid
+// points of nuclide i whose energy maps to a bucket < b (same monotone map as the query).
+__global__ void xs_build_nuclide_buckets_kernel(const double2 *grid, long n_iso, long n_gp, int n_buckets, uint32_t *bucket)
+{
+    const long total = n_iso * (n_gp + 1);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const long i = t / (n_gp + 1), k = t - i * (n_gp + 1);
+        const double2 *g = grid + 3 * i * n_gp;
+        const int b_prev = (k == 0) ? -1 : bucket_of(g[3 * (k - 1)].x, (double)n_buckets, n_buckets);
+        const int b_here = (k == n_gp) ? n_buckets : bucket_of(g[3 * k].x, (double)n_buckets, n_buckets);
+        uint32_t *row = bucket + i * (n_buckets + 1);
+        for (int b = b_prev + 1; b <= b_here; b++) row[b] = (uint32_t)k;
+    }
+}
+
 // Pair records for the window kernel (init only); record r = nuc*n_gp + k, k <= n_gp-2.
 __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp, double2 *pairs)
 {
