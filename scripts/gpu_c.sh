@@ -1,4 +1,7 @@
 #!/bin/bash
-python -m pytest tests -m "gpu and not slow" -x -q 2>&1 | tail -3
-python scripts/quick_bench.py --grid nuclide --kernels 0,4,6 XSB200_NUCLIDE_BUCKETS=1 XSB200_NUCLIDE_BUCKETS=0 2>&1 | tail -6
-python scripts/quick_bench.py --grid nuclide --method history --kernels 0 2>&1 | tail -1
+set -u
+mkdir -p gpurun_out
+python __graft_entry__.py smoke 2>&1 | tail -5
+python scripts/quick_bench.py --kernels 4,6 --reps 3 "" XSB200_KEY_LO_BIT=16 XSB200_KEY_LO_BIT=20 XSB200_KEY_LO_BIT=24 2>&1 | tail -8
+# k6 fuel window: count launches first
+ncu --set full --clock-control none --import-source on -k regex:xs_window_kernel -s 14 -c 1 -f -o gpurun_out/prof_window_k6 python scripts/quick_bench.py --kernels 6 --reps 1 2>&1 | tail -1

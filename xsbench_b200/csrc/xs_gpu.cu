@@ -485,7 +485,8 @@ int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, int n_m
     for (int i = 0; i < n_mats && rc == XS_OK; i++) {
         const int m = mats[i], n = ctx->num_nucs[m];
         int passes = (n + width - 1) / width;
-        if (passes > 1 && n - (passes - 1) * width <= xs::kMaxWindow - 32) passes--;
+        const int folded = n - (passes - 2) * width;           // size of the last window if the remainder is folded in
+        if (passes > 1 && (folded + quantum - 1) / quantum * quantum <= xs::kMaxWindow) passes--;
         if (b.count[m] <= 0) continue;
         if (passes == 1) {
             xs::WindowSegment &sgm = small.seg[small.n_seg++];

@@ -408,13 +408,14 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
 #ifndef XS_SWEEP_BLOCKS
 #define XS_SWEEP_BLOCKS 4
 #endif
-#ifndef XS_SWEEP_PREFETCH
-#define XS_SWEEP_PREFETCH 0
-#endif
 constexpr int kSweepUnroll = XS_SWEEP_UNROLL;
-constexpr int kSweepPrefetch = XS_SWEEP_PREFETCH;   // steps ahead of the register pipeline to pull records into L1
 constexpr int kSweepSlots = 8;
-constexpr int kMaxWindow = 36;             // nuclides per window (staging capacity: 32 + one step quantum)
+constexpr int kSweepQuantum = 2 * kSweepUnroll;                       // steps per trip of the gather loop
+constexpr int kFoldShift = kSweepQuantum <= 4 ? 2 : 3;                // staging row of a folded remainder
+constexpr int kMaxWindow = 32 + (1 << kFoldShift);   // nuclides per window (staging capacity: 32 + one folded quantum)
+#ifndef XS_SWEEP_FENCE
+#define XS_SWEEP_FENCE 1
+#endif
 constexpr int kMaxSegments = 12;
 
 struct WindowSegment {
@@ -439,7 +440,6 @@ struct WindowArgs {
 
 struct Quarter { double a, da, b, db; };
 
-XS_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // Asynchronous global->shared copies (LDGSTS): the next group's sample is fetched without
 // tying up registers for the duration of the current group.
@@ -463,7 +463,7 @@ XS_DEV Quarter ldg_quarter(const double2 *p)
 
 // One step: lane 3 turns (hi.E, d, 1/d) into f and broadcasts it; every lane folds its two
 // channels.  conc == 0 for padded steps.
-XS_DEV void sweep_step(const Quarter &v, double e, double conc, int f_src, double &acc_x, double &acc_y)
+XS_DEV double sweep_step(const Quarter &v, double e, double conc, int f_src, double &acc_x, double &acc_y)
 {
     const double n = v.a - e;                          // hi.E - E          (lane 3)
     const double q = n * v.b;                          // n * (1/d)
@@ -472,6 +472,22 @@ XS_DEV void sweep_step(const Quarter &v, double e, double conc, int f_src, doubl
     const double f = __shfl_sync(kFullMask, f_own, f_src);
     acc_x += (v.a - f * v.da) * conc;
     acc_y += (v.b - f * v.db) * conc;
+    return f;
+}
+
+// ptxas hoists the first consumer of a just-issued record load above the arithmetic of the
+// previous half of the loop, which turns the two-deep software pipeline into a one-deep one
+// (ncu source page: the warp then sits on that DADD for a full L2 round trip).  Making the
+// energy operand of the next half depend on a result of this half pins the order: fma(0, x, e)
+// is e exactly (x finite, e >= 0) and cannot be folded.  Measured: energy-sorted lookups
+// (-k 6) 8.76 -> 8.13 ms, unsorted (-k 4, bound by L2->SM gather throughput) unchanged.
+XS_DEV double order_after(double e, double x)
+{
+#if XS_SWEEP_FENCE
+    return __fma_rn(0.0, x, e);
+#else
+    return e;
+#endif
 }
 
 // Resolve the record numbers of one window for the 8 lookups of a warp.  The 8 x n_steps
@@ -575,8 +591,8 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             else if (n_steps <= 16) stage_records<GRID, 4>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
             else {
                 stage_records<GRID, 5>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
-                if (n_steps > 32)   // a folded remainder: steps 32..35
-                    stage_records<GRID, 2>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane, 32);
+                if (n_steps > 32)   // a folded remainder: steps 32..32 + 2^kFoldShift - 1
+                    stage_records<GRID, kFoldShift>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane, 32);
             }
         }
         __syncwarp();
@@ -588,26 +604,22 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 #pragma unroll
         for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
         int j0 = 0;
+        double e0 = e, e1 = e;
         for (; j0 + 2 * kSweepUnroll < n_steps; j0 += 2 * kSweepUnroll) {
-            if (kSweepPrefetch > 0) {
-#pragma unroll
-                for (int u = 0; u < 2 * kSweepUnroll; u++) {
-                    const int jp = j0 + kSweepPrefetch + u;
-                    if (jp < n_steps) prefetch_l1(my_pairs + 8 * (long)my_rec[jp]);
-                }
-            }
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
                 A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A0[u], e, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+                sweep_step(A0[u], e0, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+            e1 = order_after(e, acc_x);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
                 A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A1[u], e, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+                sweep_step(A1[u], e1, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+            e0 = order_after(e, acc_x);
         }
         {   // last iteration: nothing left to prefetch
 #pragma unroll
@@ -615,10 +627,11 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A0[u], e, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+                sweep_step(A0[u], e0, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+            e1 = order_after(e, acc_x);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A1[u], e, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+                sweep_step(A1[u], e1, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
         }
 
         if (!A.last_window) {
