@@ -122,6 +122,7 @@ struct xs_gpu_ctx {
     int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
     int e2e_chunks = 0;                    // host-sample pipeline depth (0 = by size)
     long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
+    int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
@@ -469,6 +470,41 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
     return XS_OK;
 }
 
+// Lane-per-lookup sweep over a batch sorted by (material, energy): every material in one launch.
+int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::BatchSink sink)
+{
+    static const WindowKernel table[3] = { xs::xs_sorted_kernel<xs::kUnionized>, xs::xs_sorted_kernel<xs::kNuclide>,
+                                           xs::xs_sorted_kernel<xs::kHash> };
+    xs::WindowArgs a{};
+    long groups = 0;
+    for (int m = 0; m < XS_NUM_MATERIALS; m++) {
+        if (b.count[m] <= 0) continue;
+        xs::WindowSegment &sgm = a.seg[a.n_seg++];
+        sgm.mat = m; sgm.first = d.h_mat_first[m]; sgm.j_begin = 0; sgm.j_end = ctx->num_nucs[m];
+        sgm.offset = b.offset[m];
+        sgm.count = (int)b.count[m];
+        sgm.group_begin = (int)groups;
+        groups += (b.count[m] + xs::kSortedGroup - 1) / xs::kSortedGroup;
+    }
+    if (groups == 0) return XS_OK;
+    a.n_groups = (int)groups;
+    a.energy = b.energy;
+    a.where = b.where;
+    a.sample_id = b.id;
+    a.first_window = a.last_window = 1;
+    WindowKernel k = table[ctx->grid_type];
+    int blocks = 0;
+    const size_t smem = (size_t)d.P.mat_total * sizeof(int);
+    int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
+    if (rc != XS_OK) return rc;
+    const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+    if (blocks > max_useful) blocks = (int)max_useful;
+    k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink);
+    CUDA_TRY(cudaGetLastError());
+    d.launches++;
+    return XS_OK;
+}
+
 // Windowed nuclide sweep over a grouped batch, for the materials in `mats`.  Materials that
 // need several windows (fuel) get one launch per window; all single-window materials share one.
 int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, int n_mats, const int *mats,
@@ -603,6 +639,7 @@ int enqueue_grouped_back(xs_gpu_ctx *ctx, DeviceState &d)
         }
         return rc;
     }
+    if (kernel_id == 6 && ctx->sorted_kernel) return launch_sorted(ctx, d, b, sink);
     int mats[XS_NUM_MATERIALS];
     for (int m = 0; m < XS_NUM_MATERIALS; m++) mats[m] = m;
     return launch_sweep(ctx, d, b, XS_NUM_MATERIALS, mats, sink);
@@ -883,6 +920,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->max_pass = std::max(1024, env_int("XSB200_MAX_PASS", 1 << 26));
     ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
+    ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);

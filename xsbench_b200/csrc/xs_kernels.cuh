@@ -671,6 +671,149 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Lane-per-lookup sweep for ENERGY-SORTED lookups (-k 6).
+//
+// Once the lookups of a material are sorted by energy, the 32 lookups of a warp sit in the same
+// or neighbouring grid intervals of every nuclide (large/fuel: ~209 lookups per interval), i.e.
+// they need the SAME pair record.  The windowed kernel above still moves 128 bytes per (lookup,
+// nuclide) through the L1 data stage -- 8 wavefronts per warp-load whatever the addresses, and
+// that is why sorting did not make it faster.  Here every lane owns one lookup and all five
+// channels; the lanes read the record with (mostly) identical addresses, which the L1 serves
+// as a broadcast: a 256-bit warp-load costs 3.4 cycles instead of 8 (scripts/exp/bcast_bench.cu),
+// i.e. 4 loads = 13 cycles per 32 (lookup, nuclide) pairs instead of 8 per 8.  No cross-lane
+// traffic at all in the gather loop: f, the five interpolations and the argmax are per lane,
+// in the reference's order and with the reference's roundings (same operations as sweep_step).
+//
+// All nuclides of a material are swept in one pass (no windows, no partial sums): at any moment
+// the resident warps cover a narrow energy band, so the records in flight fit L1/L2 by
+// construction.  Unionized grid: the index entries of 32 lookups x 32 nuclides are read as 32
+// coalesced row segments and transposed through shared memory.
+// ---------------------------------------------------------------------------------------
+#ifndef XS_SORTED_BLOCKS
+#define XS_SORTED_BLOCKS 3
+#endif
+constexpr int kSortedGroup = 32;           // lookups per warp-group
+
+struct PairRecord { double hi[5], dlt[5], hi_e, d, inv, pad; };
+
+XS_DEV PairRecord ldg_record(const double2 *rec)
+{
+    PairRecord r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.hi[0]), "=d"(r.dlt[0]), "=d"(r.hi[1]), "=d"(r.dlt[1]) : "l"(rec));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.hi[2]), "=d"(r.dlt[2]), "=d"(r.hi[3]), "=d"(r.dlt[3]) : "l"(rec + 2));
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.hi[4]), "=d"(r.dlt[4]) : "l"(rec + 4));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.hi_e), "=d"(r.d), "=d"(r.inv), "=d"(r.pad) : "l"(rec + 6));
+    return r;
+}
+
+XS_DEV void record_step(const PairRecord &r, double e, double conc, double acc[5])
+{
+    const double n = r.hi_e - e;
+    const double q = n * r.inv;
+    const double rem = __fma_rn(-r.d, q, n);
+    const double f = __fma_rn(rem, r.inv, q);          // correctly rounded (hi.E - E) / d
+#pragma unroll
+    for (int k = 0; k < 5; k++) acc[k] += (r.hi[k] - f * r.dlt[k]) * conc;
+}
+
+template <int GRID>
+__global__ void __launch_bounds__(kBlockThreads, XS_SORTED_BLOCKS)
+xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
+{
+    constexpr bool kStaged = GRID == kUnionized;
+    constexpr int kPitch = 33;                               // conflict-free column reads
+    __shared__ unsigned long long s_part[kWarpsPerBlock];
+    __shared__ uint32_t s_rec[kStaged ? kWarpsPerBlock : 1][kSortedGroup * kPitch];
+    extern __shared__ int s_nuc[];                           // [mat_total] nuclide ids of all materials
+    for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int my_sum = 0;
+    uint32_t *rec_col = s_rec[kStaged ? warp : 0] + lane;            // + i*kPitch: entry (lookup i, step lane)
+    const uint32_t *rec_row = s_rec[kStaged ? warp : 0] + lane * kPitch;   // + j: entry (lookup lane, step j)
+
+    // a block takes 8 consecutive groups: neighbouring energies share records in L1
+    for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
+        int sg = 0;
+        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;      // warp-uniform, <= 11 steps
+        const WindowSegment &S = A.seg[sg];
+        const int first_in_seg = (g - S.group_begin) * kSortedGroup;
+        const bool on = lane < S.count - first_in_seg;
+        const long t = S.offset + first_in_seg + lane;
+        const double e = on ? A.energy[t] : 0.5;
+        const uint32_t where32 = on ? A.where[t] : 0u;       // idle lanes: row 0, results dropped
+        const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
+        const int ci = S.mat * kConcStride;
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+
+        for (int c0 = 0; c0 < n_nuc; c0 += 32) {
+            const int jn = min(32, n_nuc - c0);
+            const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
+            const int *nucs = s_nuc + S.first + c0;
+            if (kStaged) {
+                // record numbers of 32 lookups x 32 steps: one coalesced index-row segment per
+                // lookup, transposed through shared memory.  Columns >= jn resolve to a valid
+                // record of nuclide 0 (never an out-of-range address, never used with conc != 0).
+                __syncwarp();
+                const int nuc_l = lane < jn ? nucs[lane] : 0;
+                const int *col = P.index_grid + nuc_l;
+                const uint32_t base_l = (uint32_t)nuc_l * (uint32_t)P.n_gp;
+#pragma unroll 16
+                for (int i = 0; i < kSortedGroup; i++) {
+                    const uint32_t w_i = __shfl_sync(kFullMask, where32, i);
+                    rec_col[i * kPitch] = base_l + (uint32_t)ldg_index_stream(col + (size_t)w_i * (uint32_t)P.n_iso);
+                }
+                __syncwarp();
+            }
+            auto record_of = [&](int j) -> const double2 * {
+                if (kStaged) return P.pairs + 8 * (size_t)rec_row[j];
+                const int nuc = nucs[min(j, jn - 1)];
+                return P.pairs + 8 * ((long)nuc * P.n_gp + nuclide_low<GRID, false>(P, e, (long)where32, nuc));
+            };
+            // two records in flight per lane, ping-pong (no register copies)
+            PairRecord ra = ldg_record(record_of(0)), rb;
+            for (int j = 0; j < n_steps; j += 2) {
+                rb = ldg_record(record_of(j + 1));
+                record_step(ra, e, c_conc_pad[ci + c0 + j], acc);
+                if (j + 2 < n_steps) ra = ldg_record(record_of(j + 2));
+                record_step(rb, e, c_conc_pad[ci + c0 + j + 1], acc);
+            }
+        }
+
+        if (on) {
+            double gap;
+            const int am = argmax5(acc, gap);
+            my_sum += (unsigned int)(am + 1);
+            if (sink.macro_out) {
+                const long id = A.sample_id ? (long)A.sample_id[t] : t;
+#pragma unroll
+                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[k];
+            }
+            if (sink.fwd_out) {            // history mode feedback (openmp-threading/Simulation.c:225-228)
+                const long id = A.sample_id ? (long)A.sample_id[t] : t;
+                int fwd = 0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) fwd += acc[k] > 1.0;
+                sink.fwd_out[id] = (unsigned char)fwd;
+            }
+        }
+    }
+    const unsigned long long bs = block_sum(my_sum, s_part);
+    if (threadIdx.x == 0) {
+        if (bs) atomicAdd(sink.accum, bs);
+        if (blockIdx.x == 0) {                               // lookups completed by this launch
+            unsigned long long done = 0;
+            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
+            atomicAdd(sink.accum + 1, done);
+        }
+    }
+}
+
 // Per-nuclide bucket tables for nuclide-grid mode (init only): bucket[i][b] = number of grid
 // points of nuclide i whose energy maps to a bucket < b (same monotone map as the query).
 __global__ void xs_build_nuclide_buckets_kernel(const double2 *grid, long n_iso, long n_gp, int n_buckets, uint32_t *bucket)
@@ -687,7 +830,10 @@ __global__ void xs_build_nuclide_buckets_kernel(const double2 *grid, long n_iso,
     }
 }
 
-// Pair records for the window kernel (init only); record r = nuc*n_gp + k, k <= n_gp-2.
+// Pair records for the sweep kernels (init only); record r = nuc*n_gp + k, k <= n_gp-2.  The
+// last slot of every nuclide (k = n_gp-1) repeats k = n_gp-2: the reference clamps an index that
+// points at the last grid point to the last interval (cuda/Simulation.cu:120-133, 159-162), and a gather
+// that reads the slot directly gets that clamp for free.
 __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp, double2 *pairs)
 {
     const long total = n_iso * n_gp;
@@ -696,9 +842,10 @@ __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp
         double2 out[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) out[i] = make_double2(0.0, 0.0);
-        if (r % n_gp + 1 < n_gp) {
-            const double2 l0 = grid[3 * r], l1 = grid[3 * r + 1], l2 = grid[3 * r + 2];
-            const double2 h0 = grid[3 * r + 3], h1 = grid[3 * r + 4], h2 = grid[3 * r + 5];
+        if (n_gp >= 2) {
+            const long lo = (r % n_gp + 1 < n_gp) ? r : r - 1;
+            const double2 l0 = grid[3 * lo], l1 = grid[3 * lo + 1], l2 = grid[3 * lo + 2];
+            const double2 h0 = grid[3 * lo + 3], h1 = grid[3 * lo + 4], h2 = grid[3 * lo + 5];
             const double d = h0.x - l0.x;
             out[0] = make_double2(h0.y, h0.y - l0.y);        // total
             out[1] = make_double2(h1.x, h1.x - l1.x);        // elastic
