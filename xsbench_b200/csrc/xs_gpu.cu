@@ -87,6 +87,8 @@ struct DeviceState {
     double *samp_e = nullptr;
     int *samp_mat = nullptr;
     uint32_t *key[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
+    unsigned int *bin_count = nullptr;     // [12 << bin_bits] fine (material, energy) bins of the -k 6 bin sort
+    unsigned int *bin_chunk_sum = nullptr; // scan scratch
     xs::SortScratch sort{};
     double2 *pairs = nullptr;              // pair records for the window kernel (128 B per grid point)
     uint32_t *nuc_bucket = nullptr;        // nuclide-grid mode: per-nuclide search tables
@@ -122,6 +124,8 @@ struct xs_gpu_ctx {
     int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
     int e2e_chunks = 0;                    // host-sample pipeline depth (0 = by size)
     long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
+    int bin_bits = 0;                      // -k 6: energy bits of the one-pass bin sort; 0 (default) = three-pass radix sort,
+                                           // which measured the same total (5.49 vs 5.56 ms) and keeps a deterministic order
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
@@ -362,7 +366,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     return XS_OK;
 }
 
-int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
+int ensure_sample_buffers(DeviceState &d, long n, bool need_sort, int bin_bits = 0)
 {
     CUDA_TRY(cudaSetDevice(d.device));
     if (n > d.sample_capacity) {
@@ -394,6 +398,11 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort)
         CUDA_TRY(cudaMalloc(&d.hist_fwd, cap));
         int rc = xs::sort_scratch_alloc(d.sort, d.sample_capacity);
         if (rc != 0) return set_error(XS_ERR_CUDA, "sort scratch allocation failed");
+    }
+    if (need_sort && bin_bits > 0 && !d.bin_count) {
+        const size_t n_bins = (size_t)XS_NUM_MATERIALS << bin_bits;
+        CUDA_TRY(cudaMalloc(&d.bin_count, n_bins * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&d.bin_chunk_sum, (n_bins / xs::kScanChunk + 1) * sizeof(unsigned int)));
     }
     return XS_OK;
 }
@@ -494,7 +503,10 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
     a.first_window = a.last_window = 1;
     WindowKernel k = table[ctx->grid_type];
     int blocks = 0;
-    const size_t smem = (size_t)d.P.mat_total * sizeof(int);
+    const size_t staged = ctx->grid_type == XS_UNIONIZED
+                              ? (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes) : 0;
+    const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
+    CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
     if (rc != XS_OK) return rc;
     const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
@@ -548,10 +560,14 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
                   bool with_hist)
 {
     int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
+    const bool with_bins = with_key && ctx->bin_bits > 0;
+    if (with_bins)
+        CUDA_TRY(cudaMemsetAsync(d.bin_count, 0, ((size_t)XS_NUM_MATERIALS << ctx->bin_bits) * sizeof(unsigned int), d.stream));
     xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_id, count, d.samp_e, d.samp_mat,
                                                        with_where ? d.samp_where : nullptr,
                                                        with_key ? d.key[0] : nullptr,
-                                                       with_hist ? d.histogram : nullptr);
+                                                       with_hist ? d.histogram : nullptr,
+                                                       with_bins ? d.bin_count : nullptr, 28 - ctx->bin_bits);
     CUDA_TRY(cudaGetLastError());
     d.launches++;
     return XS_OK;
@@ -568,8 +584,21 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
 {
     CUDA_TRY(cudaSetDevice(d.device));
     const uint32_t *id = nullptr;
-    if (kernel_id == 6) {
-        // optimization 6 (cuda/Simulation.cu:1024-1099): sort by (material, energy)
+    if (kernel_id == 6 && ctx->bin_bits > 0) {
+        // optimization 6 (cuda/Simulation.cu:1024-1099): order by (material, energy) -- one-pass bin
+        // sort on the fine histogram the sampler counted
+        const long n_bins = (long)XS_NUM_MATERIALS << ctx->bin_bits;
+        const int n_chunks = (int)((n_bins + xs::kScanChunk - 1) / xs::kScanChunk);
+        xs::sort_chunk_sum_kernel<<<n_chunks, xs::kScanThreads, 0, d.stream>>>(d.bin_count, n_bins, d.bin_chunk_sum);
+        xs::sort_scan_kernel<<<n_chunks, xs::kScanThreads, 0, d.stream>>>(d.bin_count, n_bins, d.bin_chunk_sum);
+        const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
+        xs::xs_bin_scatter_kernel<<<blocks, 256, 0, d.stream>>>(d.key[0], d.samp_e, d.samp_where, count, d.bin_count,
+                                                               28 - ctx->bin_bits, d.grp_e, d.grp_where, d.grp_id);
+        CUDA_TRY(cudaGetLastError());
+        d.launches += 3;
+        id = d.grp_id;
+    } else if (kernel_id == 6) {
+        // the same order from a stable three-pass radix sort + gather (XSB200_BIN_BITS=0)
         uint32_t *sorted_perm = nullptr;
         int rc = xs::sort_lookups(d.sort, d.key, d.perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
         if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -737,7 +766,7 @@ int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long firs
         rc = launch_event(ctx, d, src, sink, 0);
     } else {
         const bool sorted = kernel_id == 4 || kernel_id == 5 || kernel_id == 6;
-        if ((rc = ensure_sample_buffers(d, count, sorted)) != XS_OK) return rc;
+        if ((rc = ensure_sample_buffers(d, count, sorted, ctx->bin_bits)) != XS_OK) return rc;
         if ((rc = launch_sample(ctx, d, first_id, count, sorted, kernel_id == 6, sorted)) != XS_OK) return rc;
         if (first_pass) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
         src.energy = d.samp_e;
@@ -921,6 +950,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
+    ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);
@@ -945,7 +975,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
         // pre-allocate the sample / sort buffers here, not inside the timed region
         const long per_gpu = ((long)in->lookups + n_gpus - 1) / n_gpus;
         for (int g = 0; g < n_gpus && rc == XS_OK; g++)
-            rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4);
+            rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4, ctx->bin_bits);
     }
     if (rc == XS_OK && n_gpus > 1) rc = xs_multi_init(ctx);
     if (rc != XS_OK) {
@@ -1184,6 +1214,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         cudaFree(d.accum); cudaFree(d.counters); cudaFree(d.histogram);
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
+        cudaFree(d.bin_count); cudaFree(d.bin_chunk_sum);
         xs::sort_scratch_free(d.sort);
         cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
         cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd); cudaFree(d.nuc_bucket);

@@ -691,11 +691,52 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 // coalesced row segments and transposed through shared memory.
 // ---------------------------------------------------------------------------------------
 #ifndef XS_SORTED_BLOCKS
-#define XS_SORTED_BLOCKS 3
+#define XS_SORTED_BLOCKS 2
 #endif
-constexpr int kSortedGroup = 32;           // lookups per warp-group
+#ifndef XS_SORTED_PER_LANE
+#define XS_SORTED_PER_LANE 2
+#endif
+// A lane owns kPerLane CONSECUTIVE lookups: they almost always share the record too (large/fuel:
+// 99.5 % per nuclide), so one record load serves them all and the bytes moved into registers
+// per (lookup, nuclide) -- the L1 data stage is the busiest unit of this kernel -- drop by
+// kPerLane; a lane whose next lookup sits in the next grid interval reloads (rare, divergent).
+#ifndef XS_SORTED_STAGE_PF
+#define XS_SORTED_STAGE_PF 1       // prefetch a chunk's records into L2 at staging time (3.62 vs 4.07 ms; an in-loop L1 prefetch made it slower)
+#endif
+constexpr int kPerLane = XS_SORTED_PER_LANE;
+XS_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+constexpr int kSortedGroup = 32 * kPerLane;        // lookups per warp-group
+constexpr int kLaneWords = 32 * kPerLane + 1;      // staged record numbers of one lane: [which][step] + pad (bank = lane + step)
+
+#ifndef XS_SORTED_RING
+#define XS_SORTED_RING 8
+#endif
+constexpr int kRing = XS_SORTED_RING;              // steps of records in flight per warp (cp.async ring in shared memory)
+constexpr int kRingBytes = kRing * 2 * 128;        // per warp: [step % kRing][first | last lookup's record][128 B]
 
 struct PairRecord { double hi[5], dlt[5], hi_e, d, inv, pad; };
+
+XS_DEV void cp_async_16(uint32_t smem_addr, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gmem));
+}
+XS_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> XS_DEV void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// A record from the ring: all lanes of a warp read the same 128 bytes (broadcast, 7 LDS.128).
+XS_DEV PairRecord lds_record(uint32_t smem_addr)
+{
+    PairRecord r;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.hi[0]), "=d"(r.dlt[0]) : "r"(smem_addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(r.hi[1]), "=d"(r.dlt[1]) : "r"(smem_addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+32];" : "=d"(r.hi[2]), "=d"(r.dlt[2]) : "r"(smem_addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+48];" : "=d"(r.hi[3]), "=d"(r.dlt[3]) : "r"(smem_addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+64];" : "=d"(r.hi[4]), "=d"(r.dlt[4]) : "r"(smem_addr));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+96];" : "=d"(r.hi_e), "=d"(r.d) : "r"(smem_addr));
+    asm volatile("ld.shared.f64 %0, [%1+112];" : "=d"(r.inv) : "r"(smem_addr));
+    r.pad = 0.0;
+    return r;
+}
 
 XS_DEV PairRecord ldg_record(const double2 *rec)
 {
@@ -725,80 +766,178 @@ __global__ void __launch_bounds__(kBlockThreads, XS_SORTED_BLOCKS)
 xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 {
     constexpr bool kStaged = GRID == kUnionized;
-    constexpr int kPitch = 33;                               // conflict-free column reads
     __shared__ unsigned long long s_part[kWarpsPerBlock];
-    __shared__ uint32_t s_rec[kStaged ? kWarpsPerBlock : 1][kSortedGroup * kPitch];
-    extern __shared__ int s_nuc[];                           // [mat_total] nuclide ids of all materials
+    extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][staged record numbers][nuclide ids]
+    uint32_t *s_rec = s_dyn + (kStaged ? kWarpsPerBlock * kRingBytes / 4 : 0);
+    int *s_nuc = (int *)(s_rec + (kStaged ? kWarpsPerBlock * 32 * kLaneWords : 0));
     for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int my_sum = 0;
-    uint32_t *rec_col = s_rec[kStaged ? warp : 0] + lane;            // + i*kPitch: entry (lookup i, step lane)
-    const uint32_t *rec_row = s_rec[kStaged ? warp : 0] + lane * kPitch;   // + j: entry (lookup lane, step j)
+    uint32_t *warp_rec = s_rec + (kStaged ? warp * 32 * kLaneWords : 0);
+    const uint32_t *my_rec = warp_rec + lane * kLaneWords;   // [which * 32 + step]
+    const uint32_t *first_rec = warp_rec;                                        // lookup 0 of the group
+    const uint32_t *last_rec = warp_rec + 31 * kLaneWords + (kPerLane - 1) * 32;  // its last lookup
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + (kStaged ? warp * kRingBytes : 0);
 
     // a block takes 8 consecutive groups: neighbouring energies share records in L1
     for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
         int sg = 0;
         while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;      // warp-uniform, <= 11 steps
         const WindowSegment &S = A.seg[sg];
-        const int first_in_seg = (g - S.group_begin) * kSortedGroup;
-        const bool on = lane < S.count - first_in_seg;
-        const long t = S.offset + first_in_seg + lane;
-        const double e = on ? A.energy[t] : 0.5;
-        const uint32_t where32 = on ? A.where[t] : 0u;       // idle lanes: row 0, results dropped
+        const int first_in_seg = (g - S.group_begin) * kSortedGroup + lane * kPerLane;
+        const long t0 = S.offset + first_in_seg;
+        double e[kPerLane];
+        uint32_t where32[kPerLane];
+        bool on[kPerLane];
+#pragma unroll
+        for (int w = 0; w < kPerLane; w++) {
+            on[w] = first_in_seg + w < S.count;
+            // idle slots repeat the segment's last lookup (results dropped): the group's last
+            // lookup then still bounds the records of all the others
+            const long t = on[w] ? t0 + w : S.offset + S.count - 1;
+            e[w] = A.energy[t];
+            where32[w] = A.where[t];
+        }
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
         const int ci = S.mat * kConcStride;
-        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        double acc[kPerLane][5];
+#pragma unroll
+        for (int w = 0; w < kPerLane; w++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
 
         for (int c0 = 0; c0 < n_nuc; c0 += 32) {
             const int jn = min(32, n_nuc - c0);
             const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
             const int *nucs = s_nuc + S.first + c0;
-            if (kStaged) {
-                // record numbers of 32 lookups x 32 steps: one coalesced index-row segment per
-                // lookup, transposed through shared memory.  Columns >= jn resolve to a valid
+            if constexpr (kStaged) {
+                // record numbers of 32*kPerLane lookups x 32 steps: one coalesced index-row segment
+                // per lookup, transposed through shared memory.  Columns >= jn resolve to a valid
                 // record of nuclide 0 (never an out-of-range address, never used with conc != 0).
                 __syncwarp();
                 const int nuc_l = lane < jn ? nucs[lane] : 0;
                 const int *col = P.index_grid + nuc_l;
                 const uint32_t base_l = (uint32_t)nuc_l * (uint32_t)P.n_gp;
-#pragma unroll 16
-                for (int i = 0; i < kSortedGroup; i++) {
-                    const uint32_t w_i = __shfl_sync(kFullMask, where32, i);
-                    rec_col[i * kPitch] = base_l + (uint32_t)ldg_index_stream(col + (size_t)w_i * (uint32_t)P.n_iso);
+#pragma unroll 8
+                for (int l = 0; l < 32; l++) {
+#pragma unroll
+                    for (int w = 0; w < kPerLane; w++) {
+                        const uint32_t w_i = __shfl_sync(kFullMask, where32[w], l);
+                        const uint32_t no = base_l + (uint32_t)ldg_index_stream(col + (size_t)w_i * (uint32_t)P.n_iso);
+                        warp_rec[l * kLaneWords + w * 32 + lane] = no;
+                        // A record is used by ~one block only (neighbouring energies), so its first
+                        // touch comes from DRAM: request the records of the group's first and last
+                        // lookup (the others lie in between) for all 32 steps at once, now.
+                        if (XS_SORTED_STAGE_PF && ((l == 0 && w == 0) || (l == 31 && w == kPerLane - 1)))
+                            prefetch_l2(P.pairs + 8 * (size_t)no);
+                    }
                 }
                 __syncwarp();
-            }
-            auto record_of = [&](int j) -> const double2 * {
-                if (kStaged) return P.pairs + 8 * (size_t)rec_row[j];
-                const int nuc = nucs[min(j, jn - 1)];
-                return P.pairs + 8 * ((long)nuc * P.n_gp + nuclide_low<GRID, false>(P, e, (long)where32, nuc));
-            };
-            // two records in flight per lane, ping-pong (no register copies)
-            PairRecord ra = ldg_record(record_of(0)), rb;
-            for (int j = 0; j < n_steps; j += 2) {
-                rb = ldg_record(record_of(j + 1));
-                record_step(ra, e, c_conc_pad[ci + c0 + j], acc);
-                if (j + 2 < n_steps) ra = ldg_record(record_of(j + 2));
-                record_step(rb, e, c_conc_pad[ci + c0 + j + 1], acc);
+                if (c0 + 32 < n_nuc) {
+                    // index-row segments of the next chunk: start their trip from DRAM now
+                    const int last_col = min(63, n_nuc - c0 - 1);
+#pragma unroll
+                    for (int w = 0; w < kPerLane; w++) {
+                        const int *row = P.index_grid + (size_t)where32[w] * (uint32_t)P.n_iso;
+                        prefetch_l2(row + nucs[32]);
+                        prefetch_l2(row + nucs[last_col]);
+                    }
+                }
+
+                // ---- gather through the ring: the records of the group's first and last lookup
+                // are copied to shared memory kRing steps ahead (cp.async, 16 lanes x 16 B per
+                // step, two steps per instruction) and read back as broadcasts; a lookup whose
+                // record is neither (possible only when the group spans > 2 grid intervals of
+                // a nuclide) loads it directly.
+                auto issue = [&](int s) {                    // steps s, s+1 (s even)
+                    const int step = s + (lane >> 4);
+                    if (step < n_steps) {
+                        const int which = (lane >> 3) & 1;
+                        const uint32_t no = which ? last_rec[step] : first_rec[step];
+                        cp_async_16(ring + (uint32_t)((step % kRing) * 256 + which * 128 + (lane & 7) * 16),
+                                    P.pairs + 8 * (size_t)no + (lane & 7));
+                    }
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int s = 0; s < kRing; s += 2) issue(s);
+                for (int j = 0; j < n_steps; j += 2) {
+                    cp_async_wait_group<kRing / 2 - 1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int step = j + h;
+                        const double conc = c_conc_pad[ci + c0 + step];
+                        const uint32_t no_first = first_rec[step], no_last = last_rec[step];
+                        const uint32_t slot = ring + (uint32_t)((step % kRing) * 256);
+                        PairRecord r;
+                        uint32_t have = 0xffffffffu;
+#pragma unroll
+                        for (int w = 0; w < kPerLane; w++) {
+                            const uint32_t no = my_rec[w * 32 + step];
+                            if (no != have) {
+                                if (no == no_first)     r = lds_record(slot);
+                                else if (no == no_last) r = lds_record(slot + 128);
+                                else                    r = ldg_record(P.pairs + 8 * (size_t)no);
+                                have = no;
+                            }
+                            record_step(r, e[w], conc, acc[w]);
+                        }
+                    }
+                    __syncwarp();                            // everyone is done with these two slots
+                    issue(j + kRing);
+                }
+                cp_async_wait_group<0>();
+            } else {
+                auto record_no = [&](int j, int w) -> uint32_t {
+                    const int nuc = nucs[min(j, jn - 1)];
+                    return (uint32_t)nuc * (uint32_t)P.n_gp + (uint32_t)nuclide_low<GRID, false>(P, e[w], (long)where32[w], nuc);
+                };
+                // one step of all the lane's lookups; `r` holds the record of lookup 0 on entry
+                auto lane_step = [&](PairRecord &r, uint32_t no, int j) {
+                    const double conc = c_conc_pad[ci + c0 + j];
+                    record_step(r, e[0], conc, acc[0]);
+#pragma unroll
+                    for (int w = 1; w < kPerLane; w++) {
+                        const uint32_t no_w = record_no(j, w);
+                        if (no_w != no) { r = ldg_record(P.pairs + 8 * (size_t)no_w); no = no_w; }
+                        record_step(r, e[w], conc, acc[w]);
+                    }
+                };
+                // two records in flight per lane, ping-pong (no register copies)
+                uint32_t no_a = record_no(0, 0), no_b;
+                PairRecord ra = ldg_record(P.pairs + 8 * (size_t)no_a), rb;
+                for (int j = 0; j < n_steps; j += 2) {
+                    no_b = record_no(j + 1, 0);
+                    rb = ldg_record(P.pairs + 8 * (size_t)no_b);
+                    lane_step(ra, no_a, j);
+                    if (j + 2 < n_steps) {
+                        no_a = record_no(j + 2, 0);
+                        ra = ldg_record(P.pairs + 8 * (size_t)no_a);
+                    }
+                    lane_step(rb, no_b, j + 1);
+                }
             }
         }
 
-        if (on) {
+#pragma unroll
+        for (int w = 0; w < kPerLane; w++) {
+            if (!on[w]) continue;
             double gap;
-            const int am = argmax5(acc, gap);
+            const int am = argmax5(acc[w], gap);
             my_sum += (unsigned int)(am + 1);
             if (sink.macro_out) {
-                const long id = A.sample_id ? (long)A.sample_id[t] : t;
+                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
 #pragma unroll
-                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[k];
+                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[w][k];
             }
             if (sink.fwd_out) {            // history mode feedback (openmp-threading/Simulation.c:225-228)
-                const long id = A.sample_id ? (long)A.sample_id[t] : t;
+                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
                 int fwd = 0;
 #pragma unroll
-                for (int k = 0; k < 5; k++) fwd += acc[k] > 1.0;
+                for (int k = 0; k < 5; k++) fwd += acc[w][k] > 1.0;
                 sink.fwd_out[id] = (unsigned char)fwd;
             }
         }
@@ -869,7 +1008,7 @@ __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, double *energy, int *mat,
-                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram)
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, unsigned int *bin_count, int bin_shift)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -887,7 +1026,9 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
             energy[t] = e;
             mat[t] = m;
             if (where) where[t] = (uint32_t)locate_rt(P, grid_type, e);
-            if (key) key[t] = ((uint32_t)m << 28) | (uint32_t)(s1 >> 35);
+            const uint32_t k32 = ((uint32_t)m << 28) | (uint32_t)(s1 >> 35);
+            if (key) key[t] = k32;
+            if (bin_count) atomicAdd(bin_count + (k32 >> bin_shift), 1u);
             if (mat_histogram) atomicAdd(&s_hist[m], 1u);
             s = apply(hop, s);
         }
@@ -1004,7 +1145,29 @@ xs_partition_kernel(const double *energy, const int *mat, const uint32_t *where,
     }
 }
 
-// Apply a permutation (from the radix sort, -k 6): grouped copies of energy / where.
+// Bin sort of -k 6 (default): the key (material, energy) is uniformly distributed inside a
+// material, so ONE counting pass over fine value bins (material x 2^16 energy bins, counted by the
+// sampler, exclusive-scanned in place) orders the lookups as well as the lane-per-lookup kernel
+// needs -- 36 fuel lookups per bin at "large", a sixth of a grid interval.  Every lookup takes
+// the next free slot of its bin (atomicAdd on the scanned table) and carries its payload along,
+// so the three radix passes and the random-access gather behind them (1.6 ms) become one pass.
+// The order inside a bin depends on atomic arrival order; results do not (every lookup is
+// independent, the verification is a sum).
+__global__ void __launch_bounds__(256)
+xs_bin_scatter_kernel(const uint32_t *key, const double *energy, const uint32_t *where, long count,
+                      unsigned int *bin_cursor, int bin_shift, double *out_energy, uint32_t *out_where,
+                      uint32_t *out_id)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const unsigned int at = atomicAdd(bin_cursor + (key[t] >> bin_shift), 1u);
+        out_energy[at] = energy[t];
+        out_where[at] = where[t];
+        out_id[at] = (uint32_t)t;
+    }
+}
+
+// Apply a permutation (from the radix sort, XSB200_BIN_BITS=0): grouped copies of energy / where.
 __global__ void __launch_bounds__(256)
 xs_gather_kernel(const uint32_t *perm, const double *energy, const uint32_t *where, long count,
                  double *out_energy, uint32_t *out_where)
