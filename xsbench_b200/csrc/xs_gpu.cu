@@ -505,7 +505,11 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
     int blocks = 0;
     const size_t staged = ctx->grid_type == XS_UNIONIZED
                               ? (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes) : 0;
-    const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
+    size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
+    if (ctx->grid_type == XS_UNIONIZED && ctx->sorted_kernel == 1) {
+        k = xs::xs_sorted_unionized_kernel;                 // the pipelined version
+        smem = (size_t)xs::kWarpsPerBlock * xs::kPipeWordsPerWarp * sizeof(uint32_t) + (size_t)d.P.mat_total * 2 * sizeof(int);
+    }
     CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
     if (rc != XS_OK) return rc;
