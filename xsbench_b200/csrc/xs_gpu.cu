@@ -126,6 +126,7 @@ struct xs_gpu_ctx {
     long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
     int bin_bits = 0;                      // -k 6: energy bits of the one-pass bin sort; 0 (default) = three-pass radix sort,
                                            // which measured the same total (5.49 vs 5.56 ms) and keeps a deterministic order
+    int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
@@ -505,11 +506,7 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
     int blocks = 0;
     const size_t staged = ctx->grid_type == XS_UNIONIZED
                               ? (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes) : 0;
-    size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
-    if (ctx->grid_type == XS_UNIONIZED && ctx->sorted_kernel == 1) {
-        k = xs::xs_sorted_unionized_kernel;                 // the pipelined version
-        smem = (size_t)xs::kWarpsPerBlock * xs::kPipeWordsPerWarp * sizeof(uint32_t) + (size_t)d.P.mat_total * 2 * sizeof(int);
-    }
+    const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
     CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
     if (rc != XS_OK) return rc;
@@ -588,7 +585,7 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
 {
     CUDA_TRY(cudaSetDevice(d.device));
     const uint32_t *id = nullptr;
-    if (kernel_id == 6 && ctx->bin_bits > 0) {
+    if (kernel_id == 6 && ctx->bin_bits > 0 && base == 0 && hist == d.histogram) {   // (the bins are counted by the event sampler only)
         // optimization 6 (cuda/Simulation.cu:1024-1099): order by (material, energy) -- one-pass bin
         // sort on the fine histogram the sampler counted
         const long n_bins = (long)XS_NUM_MATERIALS << ctx->bin_bits;
@@ -596,18 +593,21 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
         xs::sort_chunk_sum_kernel<<<n_chunks, xs::kScanThreads, 0, d.stream>>>(d.bin_count, n_bins, d.bin_chunk_sum);
         xs::sort_scan_kernel<<<n_chunks, xs::kScanThreads, 0, d.stream>>>(d.bin_count, n_bins, d.bin_chunk_sum);
         const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
-        xs::xs_bin_scatter_kernel<<<blocks, 256, 0, d.stream>>>(d.key[0], d.samp_e, d.samp_where, count, d.bin_count,
-                                                               28 - ctx->bin_bits, d.grp_e, d.grp_where, d.grp_id);
+        xs::xs_bin_scatter_kernel<<<blocks, 256, 0, d.stream>>>(d.key[0] + base, d.samp_e + base, d.samp_where + base, count,
+                                                               d.bin_count, 28 - ctx->bin_bits, d.grp_e + base,
+                                                               d.grp_where + base, d.grp_id + base);
         CUDA_TRY(cudaGetLastError());
         d.launches += 3;
-        id = d.grp_id;
+        id = d.grp_id + base;
     } else if (kernel_id == 6) {
         // the same order from a stable three-pass radix sort + gather (XSB200_BIN_BITS=0)
         uint32_t *sorted_perm = nullptr;
-        int rc = xs::sort_lookups(d.sort, d.key, d.perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
+        uint32_t *key[2] = { d.key[0] + base, d.key[1] + base }, *perm[2] = { d.perm[0] + base, d.perm[1] + base };
+        int rc = xs::sort_lookups(d.sort, key, perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
         if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
         const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
-        xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e, d.samp_where, count, d.grp_e, d.grp_where);
+        xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e + base, d.samp_where + base, count,
+                                                          d.grp_e + base, d.grp_where + base);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
         id = sorted_perm;
@@ -954,6 +954,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
+    ctx->e2e_kernel = env_int("XSB200_E2E_KERNEL", 6) == 4 ? 4 : 6;
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
@@ -1054,9 +1055,10 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         sink.accum = d.accum;
         if (ctx->sweep && cnt > 0) {
             // Pipelined in chunks: the host->device copy of chunk c+1 (copy stream) overlaps the
-            // row search, grouping and windowed sweep of chunk c (compute stream).  Every chunk
-            // is a complete -k 4 pipeline on its own slice of the buffers (one 64-byte histogram
-            // read-back per chunk; later copies keep running on the copy stream meanwhile).
+            // row search, sort and sweep of chunk c (compute stream).  Every chunk is a complete
+            // -k 6 (or, XSB200_E2E_KERNEL=4, -k 4) pipeline on its own slice of the buffers (one
+            // 64-byte histogram read-back per chunk; later copies keep running on the copy stream
+            // meanwhile).
             int n_chunks = ctx->e2e_chunks ? ctx->e2e_chunks : (int)std::min<long>(kMaxChunks, std::max<long>(1, cnt / 5000000));
             CUDA_TRY(cudaEventRecord(d.ev_ready, d.stream));
             CUDA_TRY(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
@@ -1071,13 +1073,14 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                 CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_copy[c], 0));
                 const int blocks = (int)std::min<long>((c_n + 255) / 256, (long)d.sm_count * 16);
                 xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
-                                                                 d.samp_where + c_lo, d.histogram + 16 * c);
+                                                                 d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
+                                                                 d.histogram + 16 * c);
                 CUDA_TRY(cudaGetLastError());
                 d.launches++;
                 if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
                 xs::BatchSink chunk_sink = sink;
                 chunk_sink.macro_out = h_macro_xs_out ? d.dump_macro + 5 * c_lo : nullptr;
-                rc = enqueue_grouped_lookup(ctx, d, 4, c_lo, c_n, d.histogram + 16 * c, d.counters + kCursorBase + 16 * c,
+                rc = enqueue_grouped_lookup(ctx, d, ctx->e2e_kernel, c_lo, c_n, d.histogram + 16 * c, d.counters + kCursorBase + 16 * c,
                                             chunk_sink, c == 0);
             }
         } else {

@@ -953,239 +953,6 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// The unionized-grid version of the sorted kernel, as one software pipeline per warp over
-// (group, chunk of 16 nuclides) items:
-//
-//   item i+1 : index entries  DRAM --cp.async--> shared   (issued at the top of item i)
-//              first/last records  --prefetch--> L2       (issued early in item i, once the
-//                                                          entries have landed)
-//   item i   : records  L2 --cp.async--> ring --LDS broadcast--> registers, kRing steps ahead
-//              FP64 interpolation + accumulation, two lookups per lane
-//
-// so neither the index rows (one DRAM round trip per chunk in the non-pipelined version: 41 % of
-// its stall samples) nor the records are waited for in steady state.  Shared memory per warp:
-// the record ring (kRing x 2 x 128 B), two index buffers (32 lanes x (2 x 16 + 1) words: lane
-// pitch 33 = conflict-free for both the row-wise cp.async writes and the column-wise reads) and
-// the group's 64 row numbers.
-// ---------------------------------------------------------------------------------------
-constexpr int kChunk = 16;                            // nuclides per pipeline item
-constexpr int kIdxPitch = kPerLane * kChunk + 1;      // words per owner lane in an index buffer
-constexpr int kIdxWords = 32 * kIdxPitch;             // per warp and buffer
-constexpr int kPipeWordsPerWarp = kRingBytes / 4 + 2 * kIdxWords + kSortedGroup;
-
-XS_DEV void cp_async_4_stream(uint32_t smem_addr, const void *gmem)   // index entries: touched once
-{
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;"
-                 :: "r"(smem_addr), "l"(gmem), "l"(policy_stream()));
-}
-
-__global__ void __launch_bounds__(kBlockThreads, XS_SORTED_BLOCKS)
-xs_sorted_unionized_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
-{
-    static_assert(kPerLane == 2 && kChunk == 16, "the staging map assumes 2 lookups per lane and 16-step chunks");
-    __shared__ unsigned long long s_part[kWarpsPerBlock];
-    extern __shared__ __align__(128) uint32_t s_dyn[];   // [per-warp pipeline state][nuclide ids][record bases]
-    int *s_nuc = (int *)(s_dyn + kWarpsPerBlock * kPipeWordsPerWarp);
-    uint32_t *s_base = (uint32_t *)(s_nuc + P.mat_total);
-    for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) {
-        s_nuc[i] = P.mat_nuc[i];
-        s_base[i] = (uint32_t)P.mat_nuc[i] * (uint32_t)P.n_gp;
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *warp_mem = s_dyn + warp * kPipeWordsPerWarp;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(warp_mem);
-    uint32_t *idx_base = warp_mem + kRingBytes / 4;                        // two buffers of kIdxWords
-    uint32_t *where_tab = warp_mem + kRingBytes / 4 + 2 * kIdxWords;      // row numbers of the group being staged
-    const int group_stride = gridDim.x * kWarpsPerBlock;
-    unsigned int my_sum = 0;
-
-    auto find_seg = [&](int gq, int hint) {
-        int sq = hint;
-        while (sq + 1 < A.n_seg && gq >= A.seg[sq + 1].group_begin) sq++;
-        return sq;
-    };
-    // The lane's kPerLane consecutive lookups of group gq.  Idle slots repeat the segment's last
-    // lookup (results dropped): the group's last lookup then still bounds the records of the rest.
-    auto load_group = [&](int gq, int sq, double (&en)[kPerLane], bool (&onn)[kPerLane], long &t0) {
-        const WindowSegment &S = A.seg[sq];
-        const int first_in_seg = (gq - S.group_begin) * kSortedGroup + lane * kPerLane;
-        t0 = S.offset + first_in_seg;
-        __syncwarp();
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++) {
-            onn[w] = first_in_seg + w < S.count;
-            const long t = onn[w] ? t0 + w : S.offset + S.count - 1;
-            en[w] = A.energy[t];
-            where_tab[kPerLane * lane + w] = A.where[t];
-        }
-        __syncwarp();
-    };
-    // cp.async the index entries of item (segment sq, chunk c0) of the group in where_tab:
-    // instruction k moves lookups 2k and 2k+1 (half-warps) x 16 columns = 32 consecutive words.
-    auto stage_issue = [&](int sq, int c0, uint32_t *buf) {
-        const WindowSegment &S = A.seg[sq];
-        const int jn = min(kChunk, S.j_end - c0);
-        const int col = lane & 15, half = lane >> 4;
-        const int *column = P.index_grid + s_nuc[S.first + c0 + min(col, jn - 1)];
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf) + 4u * lane;
-#pragma unroll 8
-        for (int k = 0; k < 32; k++)
-            cp_async_4_stream(dst + 4u * kIdxPitch * k, column + (size_t)where_tab[2 * k + half] * (uint32_t)P.n_iso);
-    };
-    // L2 prefetch of the records of the first (lanes 0-15) and last (lanes 16-31) lookup of a staged item
-    auto prefetch_records = [&](int sq, int c0, const uint32_t *buf) {
-        const WindowSegment &S = A.seg[sq];
-        const int jn = min(kChunk, S.j_end - c0);
-        const int col = lane & 15;
-        const uint32_t *entry = (lane >> 4) ? buf + 31 * kIdxPitch + (kPerLane - 1) * kChunk : buf;
-        const uint32_t no = s_base[S.first + c0 + min(col, jn - 1)] + entry[col];
-        prefetch_l2(P.pairs + 8 * (size_t)no);
-    };
-
-    int g = blockIdx.x * kWarpsPerBlock + warp;
-    if (g < A.n_groups) {
-        int sg = find_seg(g, 0), c0 = 0, buf = 0;
-        double e[kPerLane], e_nxt[kPerLane];
-        bool on[kPerLane], on_nxt[kPerLane];
-        long t0, t0_nxt = 0;
-        load_group(g, sg, e, on, t0);
-        stage_issue(sg, 0, idx_base);
-        cp_async_commit();
-        cp_async_wait_group<0>();
-        __syncwarp();
-        prefetch_records(sg, 0, idx_base);
-        double acc[kPerLane][5];
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++)
-#pragma unroll
-            for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++) { e_nxt[w] = 0.0; on_nxt[w] = false; }
-
-        while (true) {
-            const WindowSegment &S = A.seg[sg];
-            const int n_nuc = S.j_end;
-            const bool last_chunk = c0 + kChunk >= n_nuc;
-            // ---- next item: start its index entries on their way
-            int ng = g, nsg = sg, nc0 = c0 + kChunk;
-            bool nvalid = true;
-            if (last_chunk) {
-                ng = g + group_stride; nc0 = 0;
-                nvalid = ng < A.n_groups;
-                if (nvalid) { nsg = find_seg(ng, sg); load_group(ng, nsg, e_nxt, on_nxt, t0_nxt); }
-            }
-            if (nvalid) stage_issue(nsg, nc0, idx_base + (buf ^ 1) * kIdxWords);
-            cp_async_commit();
-            cp_async_wait_group<1>();                        // this item's entries have landed
-            __syncwarp();
-
-            // ---- this item
-            const int jn = min(kChunk, n_nuc - c0);
-            const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
-            const int ci = S.mat * kConcStride + c0;
-            const uint32_t *bases = s_base + S.first + c0;
-            const uint32_t *first_idx = idx_base + buf * kIdxWords;
-            const uint32_t *last_idx = first_idx + 31 * kIdxPitch + (kPerLane - 1) * kChunk;
-            const uint32_t *my_idx = first_idx + lane * kIdxPitch;
-            const uint32_t *next_idx = idx_base + (buf ^ 1) * kIdxWords;
-            auto issue = [&](int s) {                        // records of steps s, s+1 (s even) into the ring
-                const int step = s + (lane >> 4);
-                if (step < n_steps) {
-                    const int which = (lane >> 3) & 1;
-                    const uint32_t no = bases[min(step, jn - 1)] + (which ? last_idx[step] : first_idx[step]);
-                    cp_async_16(ring + (uint32_t)((step % kRing) * 256 + which * 128 + (lane & 7) * 16),
-                                P.pairs + 8 * (size_t)no + (lane & 7));
-                }
-                cp_async_commit();
-            };
-#pragma unroll
-            for (int s = 0; s < kRing; s += 2) issue(s);
-            bool prefetched = !nvalid;
-            for (int j = 0; j < n_steps; j += 2) {
-                cp_async_wait_group<kRing / 2 - 1>();
-                __syncwarp();
-                if (j == 2 && !prefetched) { prefetch_records(nsg, nc0, next_idx); prefetched = true; }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int step = j + h;
-                    const double conc = c_conc_pad[ci + step];
-                    const uint32_t base = bases[min(step, jn - 1)];
-                    const uint32_t no_first = base + first_idx[step], no_last = base + last_idx[step];
-                    const uint32_t slot = ring + (uint32_t)((step % kRing) * 256);
-                    // sources of the lane's two lookups: the first or the last lookup's record in
-                    // the ring (branch-free); anything else only if the group spans more than two
-                    // grid intervals of this nuclide (warp-uniform test, rare)
-                    const uint32_t no0 = base + my_idx[step], no1 = base + my_idx[kChunk + step];
-                    const uint32_t a0 = slot + (no0 == no_first ? 0u : 128u);
-                    const uint32_t a1 = slot + (no1 == no_first ? 0u : 128u);
-                    const bool odd0 = no0 != no_first && no0 != no_last, odd1 = no1 != no_first && no1 != no_last;
-                    PairRecord r = lds_record(a0);
-                    if (__any_sync(kFullMask, odd0 || odd1)) {
-                        if (odd0) r = ldg_record(P.pairs + 8 * (size_t)no0);
-                        record_step(r, e[0], conc, acc[0]);
-                        if (odd1) r = ldg_record(P.pairs + 8 * (size_t)no1);
-                        else if (odd0 || a1 != a0) r = lds_record(a1);
-                        record_step(r, e[1], conc, acc[1]);
-                    } else {
-                        record_step(r, e[0], conc, acc[0]);
-                        if (__any_sync(kFullMask, a1 != a0)) r = lds_record(a1);
-                        record_step(r, e[1], conc, acc[1]);
-                    }
-                }
-                __syncwarp();                                // everyone is done with these two ring slots
-                issue(j + kRing);
-            }
-            if (!prefetched) {                               // items shorter than four steps
-                cp_async_wait_group<0>();
-                __syncwarp();
-                prefetch_records(nsg, nc0, next_idx);
-            }
-
-            if (last_chunk) {
-#pragma unroll
-                for (int w = 0; w < kPerLane; w++) {
-                    if (on[w]) {
-                        double gap;
-                        const int am = argmax5(acc[w], gap);
-                        my_sum += (unsigned int)(am + 1);
-                        if (sink.macro_out) {
-                            const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
-#pragma unroll
-                            for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[w][k];
-                        }
-                        if (sink.fwd_out) {    // history mode feedback (openmp-threading/Simulation.c:225-228)
-                            const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
-                            int fwd = 0;
-#pragma unroll
-                            for (int k = 0; k < 5; k++) fwd += acc[w][k] > 1.0;
-                            sink.fwd_out[id] = (unsigned char)fwd;
-                        }
-                    }
-                    e[w] = e_nxt[w]; on[w] = on_nxt[w];
-#pragma unroll
-                    for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
-                }
-                t0 = t0_nxt;
-                if (!nvalid) break;
-            }
-            g = ng; sg = nsg; c0 = nc0; buf ^= 1;
-        }
-        cp_async_wait_group<0>();
-    }
-    const unsigned long long bs = block_sum(my_sum, s_part);
-    if (threadIdx.x == 0) {
-        if (bs) atomicAdd(sink.accum, bs);
-        if (blockIdx.x == 0) {                               // lookups completed by this launch
-            unsigned long long done = 0;
-            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
-            atomicAdd(sink.accum + 1, done);
-        }
-    }
-}
-
 // Per-nuclide bucket tables for nuclide-grid mode (init only): bucket[i][b] = number of grid
 // points of nuclide i whose energy maps to a bucket < b (same monotone map as the query).
 __global__ void xs_build_nuclide_buckets_kernel(const double2 *grid, long n_iso, long n_gp, int n_buckets, uint32_t *bucket)
@@ -1311,15 +1078,21 @@ xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long
 // Same bookkeeping for samples that already exist (host-provided): where + histogram.
 __global__ void __launch_bounds__(256)
 xs_locate_kernel(const Problem P, int grid_type, long count, const double *energy, const int *mat,
-                 uint32_t *where, unsigned int *mat_histogram)
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
-        where[t] = (uint32_t)locate_rt(P, grid_type, energy[t]);
-        atomicAdd(&s_hist[mat[t]], 1u);
+        const double e = energy[t];
+        const int m = mat[t];
+        where[t] = (uint32_t)locate_rt(P, grid_type, e);
+        if (key) {    // same layout as the sampler's key: material, then 28 bits monotone in the energy
+            const double scaled = fmin(fmax(e, 0.0) * 268435456.0, 268435455.0);
+            key[t] = ((uint32_t)m << 28) | (uint32_t)scaled;
+        }
+        atomicAdd(&s_hist[m], 1u);
     }
     __syncthreads();
     if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
