@@ -1,5 +1,4 @@
 #!/bin/bash
 set -u
-timeout 1200 python -m pytest tests -x -q -m "gpu and not slow" 2>&1 | tail -5
-python __graft_entry__.py smoke 2>&1 | tail -2
-python bench.py --steps 10 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_now.json; cut -c1-1500 gpurun_out/bench_now.json
+python scripts/quick_bench.py --kernels 6 --reps 3 "" XSB200_KEY_LO_BIT=12 XSB200_KEY_LO_BIT=16 2>&1 | tail -3
+timeout 1200 python -m pytest tests -x -q -m "gpu and not slow" 2>&1 | tail -3

@@ -708,9 +708,13 @@ XS_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];"
 constexpr int kSortedGroup = 32 * kPerLane;        // lookups per warp-group
 constexpr int kLaneWords = 32 * kPerLane + 1;      // staged record numbers of one lane: [which][step] + pad (bank = lane + step)
 
+#ifndef XS_SORTED_STAGE_UNROLL
+#define XS_SORTED_STAGE_UNROLL 32
+#endif
 #ifndef XS_SORTED_RING
 #define XS_SORTED_RING 8
 #endif
+constexpr int kStageUnroll = XS_SORTED_STAGE_UNROLL;   // lookups (x kPerLane index loads) in flight while staging a chunk
 constexpr int kRing = XS_SORTED_RING;              // steps of records in flight per warp (cp.async ring in shared memory)
 constexpr int kRingBytes = kRing * 2 * 128;        // per warp: [step % kRing][first | last lookup's record][128 B]
 
@@ -820,7 +824,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 const int nuc_l = lane < jn ? nucs[lane] : 0;
                 const int *col = P.index_grid + nuc_l;
                 const uint32_t base_l = (uint32_t)nuc_l * (uint32_t)P.n_gp;
-#pragma unroll 8
+#pragma unroll kStageUnroll
                 for (int l = 0; l < 32; l++) {
 #pragma unroll
                     for (int w = 0; w < kPerLane; w++) {

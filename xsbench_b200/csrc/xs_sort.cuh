@@ -140,7 +140,7 @@ sort_scan_kernel(unsigned int *data, long total, const unsigned int *chunk_sum)
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 2)
 sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                     KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, long n, int shift,
                     uint32_t mask, int nonzero_flag, const unsigned int *__restrict__ tile_base, int n_tiles)
@@ -153,23 +153,36 @@ sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict
     const unsigned lt_mask = (1u << lane) - 1u;
     const long base = (long)blockIdx.x * kSortTile + (long)warp * (32 * kSortItems);
     KeyT key[kSortItems];
+    unsigned peers[kSortItems];
     unsigned short rank[kSortItems];
 
+    // all key loads of the tile first (16 independent requests in flight per thread), then all
+    // warp votes (independent of each other), and only then the short serial chain through the
+    // per-warp digit counters: no round waits for memory or for a vote
+#pragma unroll
+    for (int r = 0; r < kSortItems; r++) {
+        const long idx = base + r * 32 + lane;
+        key[r] = idx < n ? keys_in[idx] : (KeyT)0;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; r++) {
+        const long idx = base + r * 32 + lane;
+        const uint32_t d = idx < n ? sort_digit(key[r], shift, mask, nonzero_flag) : (uint32_t)kRadix;
+        peers[r] = __match_any_sync(kFullMask, d);
+    }
 #pragma unroll
     for (int r = 0; r < kSortItems; r++) {
         const long idx = base + r * 32 + lane;
         const bool valid = idx < n;
-        key[r] = valid ? keys_in[idx] : (KeyT)0;
         const uint32_t d = valid ? sort_digit(key[r], shift, mask, nonzero_flag) : (uint32_t)kRadix;
-        const unsigned peers = __match_any_sync(kFullMask, d);
-        const int leader = __ffs(peers) - 1;
+        const int leader = __ffs(peers[r]) - 1;
         unsigned int before = 0;
         if (valid && lane == leader) {
             before = warp_cnt[warp][d];
-            warp_cnt[warp][d] = before + __popc(peers);
+            warp_cnt[warp][d] = before + __popc(peers[r]);
         }
         before = __shfl_sync(kFullMask, before, leader);
-        rank[r] = (unsigned short)(before + __popc(peers & lt_mask));
+        rank[r] = (unsigned short)(before + __popc(peers[r] & lt_mask));
         __syncwarp();
     }
     __syncthreads();
@@ -184,6 +197,12 @@ sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict
         }
     }
     __syncthreads();
+    uint32_t val[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; r++) {
+        const long idx = base + r * 32 + lane;
+        val[r] = (vals_in && idx < n) ? vals_in[idx] : (uint32_t)idx;
+    }
 #pragma unroll
     for (int r = 0; r < kSortItems; r++) {
         const long idx = base + r * 32 + lane;
@@ -191,7 +210,7 @@ sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict
             const uint32_t d = sort_digit(key[r], shift, mask, nonzero_flag);
             const unsigned int pos = warp_cnt[warp][d] + rank[r];
             keys_out[pos] = key[r];
-            vals_out[pos] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            vals_out[pos] = val[r];
         }
     }
 }
