@@ -10,7 +10,8 @@
 // stable, so equal keys keep lookup-id order.
 //
 // Each pass = histogram (per 4096-key tile) -> exclusive scan of the digit-major
-// [digit][tile] table -> stable scatter using warp match_any ranking.
+// [digit][tile] table -> stable scatter using warp match_any ranking; 32-bit keys are reordered
+// inside the tile (shared memory) before they are written, so the global writes are runs.
 #pragma once
 
 #include "xs_device.cuh"
@@ -186,31 +187,85 @@ sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict
         __syncwarp();
     }
     __syncthreads();
-    {   // per digit: warp offsets within the tile + the tile's global base
-        const int d = threadIdx.x;
-        unsigned int run = tile_base[(long)d * n_tiles + blockIdx.x];
+    if constexpr (sizeof(KeyT) == 4) {
+        // 32-bit keys (the lookup sort): reorder the tile in shared memory first, then write it out
+        // in tile order -- consecutive threads then write consecutive addresses of one digit's run
+        // instead of 32 scattered words per store instruction.
+        __shared__ KeyT s_key[kSortTile];
+        __shared__ uint32_t s_val[kSortTile];
+        __shared__ unsigned int s_gbase[kRadix];            // global position of a digit's run minus its start in the tile
+        __shared__ unsigned int s_warp_tot[kSortWarps];
+        const int d = threadIdx.x;                          // kSortThreads == kRadix
+        unsigned int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) tot += warp_cnt[w][d];
+        unsigned int incl = tot;                            // exclusive scan of the 256 digit totals
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int t = __shfl_up_sync(kFullMask, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned int start = incl - tot;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) start += w < warp ? s_warp_tot[w] : 0u;
+        s_gbase[d] = tile_base[(long)d * n_tiles + blockIdx.x] - start;
+        unsigned int run = start;
 #pragma unroll
         for (int w = 0; w < kSortWarps; w++) {
             const unsigned int c = warp_cnt[w][d];
             warp_cnt[w][d] = run;
             run += c;
         }
-    }
-    __syncthreads();
-    uint32_t val[kSortItems];
+        __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
-        const long idx = base + r * 32 + lane;
-        val[r] = (vals_in && idx < n) ? vals_in[idx] : (uint32_t)idx;
-    }
+        for (int r = 0; r < kSortItems; r++) {
+            const long idx = base + r * 32 + lane;
+            if (idx < n) {
+                const uint32_t dg = sort_digit(key[r], shift, mask, nonzero_flag);
+                const unsigned int at = warp_cnt[warp][dg] + rank[r];
+                s_key[at] = key[r];
+                s_val[at] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            }
+        }
+        __syncthreads();
+        const long tile_first = (long)blockIdx.x * kSortTile;
+        const int in_tile = (int)((n - tile_first < kSortTile) ? n - tile_first : kSortTile);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < in_tile; i += kSortThreads) {
+            const KeyT k = s_key[i];
+            const unsigned int pos = s_gbase[sort_digit(k, shift, mask, nonzero_flag)] + (unsigned int)i;
+            keys_out[pos] = k;
+            vals_out[pos] = s_val[i];
+        }
+    } else {
+        {   // per digit: warp offsets within the tile + the tile's global base
+            const int d = threadIdx.x;
+            unsigned int run = tile_base[(long)d * n_tiles + blockIdx.x];
 #pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
-        const long idx = base + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = sort_digit(key[r], shift, mask, nonzero_flag);
-            const unsigned int pos = warp_cnt[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            for (int w = 0; w < kSortWarps; w++) {
+                const unsigned int c = warp_cnt[w][d];
+                warp_cnt[w][d] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        uint32_t val[kSortItems];
+#pragma unroll
+        for (int r = 0; r < kSortItems; r++) {
+            const long idx = base + r * 32 + lane;
+            val[r] = (vals_in && idx < n) ? vals_in[idx] : (uint32_t)idx;
+        }
+#pragma unroll
+        for (int r = 0; r < kSortItems; r++) {
+            const long idx = base + r * 32 + lane;
+            if (idx < n) {
+                const uint32_t d = sort_digit(key[r], shift, mask, nonzero_flag);
+                const unsigned int pos = warp_cnt[warp][d] + rank[r];
+                keys_out[pos] = key[r];
+                vals_out[pos] = val[r];
+            }
         }
     }
 }
