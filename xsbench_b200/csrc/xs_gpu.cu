@@ -108,7 +108,7 @@ struct DeviceState {
     int launches = 0;
     // a grouped batch whose histogram read-back has been enqueued but not yet consumed
     struct Pending { bool active = false; int kernel_id = 0; long base = 0, count = 0; const uint32_t *id = nullptr;
-                     xs::BatchSink sink{}; } pending;
+                     bool indirect = false; xs::BatchSink sink{}; } pending;
 };
 
 }  // namespace
@@ -126,6 +126,7 @@ struct xs_gpu_ctx {
     long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
     int bin_bits = 0;                      // -k 6: energy bits of the one-pass bin sort; 0 (default) = three-pass radix sort,
                                            // which measured the same total (5.49 vs 5.56 ms) and keeps a deterministic order
+    int fuse_gather = 1;                   // -k 6: the lookup kernel reads its samples through the sort's permutation
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
@@ -445,6 +446,7 @@ struct GroupedBatch {
     const double *energy;          // grouped by material
     const uint32_t *where;
     const uint32_t *id;            // original sample index per slot (macro_xs dumps)
+    bool indirect;                 // energy / where are still in sample order: the kernel reads them through id
     double2 *partial;
     long offset[XS_NUM_MATERIALS]; // first slot of each material (host copy of the histogram prefix)
     long count[XS_NUM_MATERIALS];  // lookups per material
@@ -501,6 +503,7 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
     a.energy = b.energy;
     a.where = b.where;
     a.sample_id = b.id;
+    a.indirect = b.indirect;
     a.first_window = a.last_window = 1;
     WindowKernel k = table[ctx->grid_type];
     int blocks = 0;
@@ -585,6 +588,7 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
 {
     CUDA_TRY(cudaSetDevice(d.device));
     const uint32_t *id = nullptr;
+    bool indirect = false;
     if (kernel_id == 6 && ctx->bin_bits > 0 && base == 0 && hist == d.histogram) {   // (the bins are counted by the event sampler only)
         // optimization 6 (cuda/Simulation.cu:1024-1099): order by (material, energy) -- one-pass bin
         // sort on the fine histogram the sampler counted
@@ -605,11 +609,15 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
         uint32_t *key[2] = { d.key[0] + base, d.key[1] + base }, *perm[2] = { d.perm[0] + base, d.perm[1] + base };
         int rc = xs::sort_lookups(d.sort, key, perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
         if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
-        const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
-        xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e + base, d.samp_where + base, count,
-                                                          d.grp_e + base, d.grp_where + base);
-        CUDA_TRY(cudaGetLastError());
-        d.launches++;
+        if (ctx->sorted_kernel && ctx->fuse_gather) {
+            indirect = true;          // the lane-per-lookup kernel applies the permutation itself
+        } else {
+            const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
+            xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e + base, d.samp_where + base, count,
+                                                              d.grp_e + base, d.grp_where + base);
+            CUDA_TRY(cudaGetLastError());
+            d.launches++;
+        }
         id = sorted_perm;
     } else {
         // optimization 4 (:754-821): group by material; optimization 5 (:895-958): fuel first
@@ -631,6 +639,7 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
     d.pending.base = base;
     d.pending.count = count;
     d.pending.id = id;
+    d.pending.indirect = indirect;
     d.pending.sink = sink;
     return XS_OK;
 }
@@ -646,8 +655,9 @@ int enqueue_grouped_back(xs_gpu_ctx *ctx, DeviceState &d)
     CUDA_TRY(cudaSetDevice(d.device));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
     GroupedBatch b{};
-    b.energy = d.grp_e + base;
-    b.where = d.grp_where + base;
+    b.indirect = d.pending.indirect;
+    b.energy = (b.indirect ? d.samp_e : d.grp_e) + base;
+    b.where = (b.indirect ? d.samp_where : d.grp_where) + base;
     b.partial = d.sweep_partial + 3 * base;
     b.id = d.pending.id;
     long offset = 0;
@@ -955,6 +965,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
     ctx->e2e_kernel = env_int("XSB200_E2E_KERNEL", 6) == 4 ? 4 : 6;
+    ctx->fuse_gather = env_int("XSB200_FUSE_GATHER", 1);
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
