@@ -226,6 +226,32 @@ def test_gather_variants_agree(monkeypatch):
     assert sums[0] == sums[1] == ol.OracleProblem(68, 1000, 0, 500).event(0, 50000, NTHREADS)
 
 
+# ---- every way through the -k 6 pipeline gives the same integers -----------------------------------------
+@pytest.mark.parametrize("env", [
+    {"XSB200_BIN_BITS": "14"},          # one-pass bin sort instead of the radix sort
+    {"XSB200_FUSE_GATHER": "0"},        # separate gather pass instead of indirect reads in the kernel
+    {"XSB200_SORTED_KERNEL": "0"},      # windowed sweep on the sorted batch
+    {"XSB200_KEY_LO_BIT": "26"},        # barely sorted: groups span many grid intervals -> direct-load path
+    {"XSB200_E2E_KERNEL": "4"},         # host-sample API through partition + windowed sweep
+])
+@pytest.mark.parametrize("grid,hb", [("unionized", 500), ("hash", 500), ("nuclide", 500)])
+def test_sorted_pipeline_variants_agree(monkeypatch, env, grid, hb):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    p = Problem("small", 1000, grid, hb, method="event", lookups=100000)
+    try:
+        inp = xs.make_inputs(size="small", grid=grid, gridpoints=1000, hash_bins=hb, method="event", lookups=100000, kernel_id=6)
+        assert p.gpu.run(inp).verification == 302880
+        rng = np.random.default_rng(3)
+        n = 70_001
+        e = rng.random(n); m = rng.integers(0, 12, n).astype(np.int32)
+        res, macro = p.gpu.lookup_samples(e, m, want_macro_xs=True)
+        v, omacro = p.oracle.lookup_samples(e, m)
+        assert res.verification == v and np.array_equal(macro, omacro)
+    finally:
+        p.close()
+
+
 # ---- device-side generator: byte-identical to the host generator --------------------------------------------
 @pytest.mark.parametrize("size,n_gp,grid,hb", [("small", 1000, "unionized", 10000), ("small", 1000, "hash", 500),
                                                ("small", 1000, "nuclide", 10000), ("large", 300, "unionized", 10000),

@@ -89,6 +89,7 @@ struct DeviceState {
     uint32_t *key[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     unsigned int *bin_count = nullptr;     // [12 << bin_bits] fine (material, energy) bins of the -k 6 bin sort
     unsigned int *bin_chunk_sum = nullptr; // scan scratch
+    bool bins_ready = false;               // the event sampler has just counted bin_count for the batch being regrouped
     xs::SortScratch sort{};
     double2 *pairs = nullptr;              // pair records for the window kernel (128 B per grid point)
     uint32_t *nuc_bucket = nullptr;        // nuclide-grid mode: per-nuclide search tables
@@ -572,6 +573,7 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
                                                        with_key ? d.key[0] : nullptr,
                                                        with_hist ? d.histogram : nullptr,
                                                        with_bins ? d.bin_count : nullptr, 28 - ctx->bin_bits);
+    d.bins_ready = with_bins;
     CUDA_TRY(cudaGetLastError());
     d.launches++;
     return XS_OK;
@@ -589,7 +591,8 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
     CUDA_TRY(cudaSetDevice(d.device));
     const uint32_t *id = nullptr;
     bool indirect = false;
-    if (kernel_id == 6 && ctx->bin_bits > 0 && base == 0 && hist == d.histogram) {   // (the bins are counted by the event sampler only)
+    if (kernel_id == 6 && d.bins_ready) {   // (the bins are counted by the event sampler only)
+        d.bins_ready = false;
         // optimization 6 (cuda/Simulation.cu:1024-1099): order by (material, energy) -- one-pass bin
         // sort on the fine histogram the sampler counted
         const long n_bins = (long)XS_NUM_MATERIALS << ctx->bin_bits;
