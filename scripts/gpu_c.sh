@@ -1,3 +1,4 @@
 #!/bin/bash
 set -u
-timeout 1500 python -m pytest tests -x -q -m "gpu and not slow" 2>&1 | tail -5
+python scripts/quick_bench.py --kernels 6 --reps 3 2>&1 | tail -1
+KERNELS=6 bash scripts/gpu_variants.sh p1b4 p1b3

@@ -1073,7 +1073,7 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
             // -k 6 (or, XSB200_E2E_KERNEL=4, -k 4) pipeline on its own slice of the buffers (one
             // 64-byte histogram read-back per chunk; later copies keep running on the copy stream
             // meanwhile).
-            int n_chunks = ctx->e2e_chunks ? ctx->e2e_chunks : (int)std::min<long>(kMaxChunks, std::max<long>(1, cnt / 5000000));
+            int n_chunks = ctx->e2e_chunks ? ctx->e2e_chunks : (int)std::min<long>(kMaxChunks, std::max<long>(1, cnt / 8000000));
             CUDA_TRY(cudaEventRecord(d.ev_ready, d.stream));
             CUDA_TRY(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
             for (int c = 0; c < n_chunks; c++) {
