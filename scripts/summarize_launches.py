@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (csv from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
-dram__bytes_write.sum --csv`) of bench.py: per-kernel share of ONE timed step of the -k 4 pipeline.
-usage: summarize_launches.py profiles/rNN_launches.csv rNN"""
+dram__bytes_write.sum --csv`) of bench.py: per-kernel share of ONE timed step of the headline
+pipeline (-k 6: sample -> radix sort -> lane-per-lookup kernel).
+usage: summarize_launches.py profiles/rNN_launches.csv rNN [bound-summary text]"""
 import collections, csv, json, os, sys
 path, tag = sys.argv[1], sys.argv[2]
+bound = sys.argv[3] if len(sys.argv) > 3 else None
 out_dir = os.path.dirname(os.path.abspath(path))
 rows = [r for r in csv.reader(open(path)) if len(r) > 5]
 hdr = rows[0]
@@ -13,15 +15,16 @@ for r in rows[1:]:
     d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(',', ''))
 launches = list(d.items())
 names = [k[1] for k, _ in launches]
-starts = [i for i, n in enumerate(names) if n.startswith('xs::xs_sample_kernel')]
+STEP = ('xs_sample_kernel', 'sort_', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel')
+starts = [i for i, n in enumerate(names) if 'xs_sample_kernel' in n]
 i0 = starts[2]                                   # steps: warm-up, timed 1, timed 2 -> take timed 2
-i1 = i0
-while i1 < len(launches) and any(t in names[i1] for t in ('xs_sample_kernel', 'xs_partition_kernel', 'xs_window_kernel')) and (i1 == i0 or 'xs_sample_kernel' not in names[i1]):
+i1 = i0 + 1
+while i1 < len(launches) and any(t in names[i1] for t in STEP) and 'xs_sample_kernel' not in names[i1]:
     i1 += 1
 st = launches[i0:i1]
 agg = collections.OrderedDict()
 for (i, n), m in st:
-    short = n.split('(')[0].replace('void ', '')
+    short = n.split('(')[0].replace('void ', '').replace('xs::', '')
     a = agg.setdefault(short, [0, 0.0, 0.0, 0.0])
     a[0] += 1; a[1] += m['gpu__time_duration.sum']; a[2] += m['dram__bytes_read.sum']; a[3] += m['dram__bytes_write.sum']
 tot = sum(a[1] for a in agg.values())
@@ -32,18 +35,18 @@ L = [f"# {tag} launch list summary: one timed step of `python bench.py --steps 2
 for k, a in agg.items():
     L.append(f"| `{k}` | {a[0]} | {a[1]/1e3:.1f} | {100*a[1]/tot:.1f} % | {a[2]/1e6:.1f} | {a[3]/1e6:.1f} |")
 L.append(f"| **total** | {sum(a[0] for a in agg.values())} | {tot/1e3:.1f} | 100 % | {sum(a[2] for a in agg.values())/1e6:.1f} | {sum(a[3] for a in agg.values())/1e6:.1f} |")
-w = [v for k, v in agg.items() if 'window' in k][0]
-L += ["", f"Window kernel: {w[0]} launches per step (fuel windows + 1 launch for the other 11 materials), {100*w[1]/tot:.1f} % of the step; "
-      f"DRAM traffic {(w[2]+w[3])/1e9:.2f} GB per step against 97.1 GB of algorithmic gather bytes (SURVEY 8d): the pair records are served "
-      "from L2; DRAM streams the index rows, samples and partial sums.", "", "Per-launch detail of that step:", ""]
+dom_name, w = max(agg.items(), key=lambda kv: kv[1][1])
+L += ["", f"Dominant kernel `{dom_name}`: {w[0]} launch(es) per step, {100*w[1]/tot:.1f} % of the step; DRAM traffic "
+      f"{(w[2]+w[3])/1e9:.2f} GB per launch against 97.1 GB of algorithmic gather bytes (SURVEY 8d): the pair records are shared by "
+      "the lookups of a warp and served from L1/L2; DRAM streams the index rows and the (randomly placed) samples.",
+      "", "Per-launch detail of that step:", ""]
 for (i, n), m in st:
     L.append(f"- #{i} `{n.split('(')[0].replace('void ', '')}`: {m['gpu__time_duration.sum']/1e3:.1f} us, DRAM read {m['dram__bytes_read.sum']/1e6:.0f} MB, write {m['dram__bytes_write.sum']/1e6:.0f} MB")
 open(os.path.join(out_dir, f"{tag}_launches_summary.md"), 'w').write("\n".join(L) + "\n")
-json.dump({"kernel": "xs_window_kernel<unionized>: all launches of one step (fuel windows + 1 launch for the other 11 materials)",
-           "dram_bytes_per_launch": w[2] + w[3], "launches_per_step": w[0], "window_kernel_share_of_step": w[1] / tot,
-           "what_bounds_it": "ncu --set full of one fuel window (profiles/%s_window_kernel_ncu.txt): l1tex__throughput 81 %%, "
-                             "lts__throughput 70 %%, L2 hit 89 %%, issue slots 49 %% -- the L1 data path, not HBM" % tag,
+json.dump({"kernel": f"{dom_name}: {w[0]} launch(es) per step",
+           "dram_bytes_per_launch": (w[2] + w[3]) / w[0], "launches_per_step": w[0], "share_of_step": w[1] / tot,
+           "what_bounds_it": bound or "see profiles/%s_notes.md" % tag,
            "source": f"profiles/{os.path.basename(path)} (ncu, one timed step of bench.py)",
            "dram_bytes_per_step_all_kernels": sum(a[2] + a[3] for a in agg.values())},
           open(os.path.join(out_dir, "lookup_kernel_traffic.json"), 'w'), indent=1)
-print("\n".join(L[:14]))
+print("\n".join(L[:20]))
