@@ -1,4 +1,3 @@
 #!/bin/bash
 set -u
-python scripts/quick_bench.py --kernels 6 --reps 3 2>&1 | tail -1
-KERNELS=6 bash scripts/gpu_variants.sh p1b4 p1b3
+python scripts/quick_bench.py --kernels 6 --reps 3 "" XSB200_FUSE_GATHER=2 XSB200_FUSE_GATHER=0 2>&1 | tail -3
