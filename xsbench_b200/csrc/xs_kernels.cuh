@@ -19,6 +19,7 @@
 #pragma once
 
 #include "xs_device.cuh"
+#include <type_traits>
 
 namespace xs {
 
@@ -825,6 +826,34 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 // per lookup, transposed through shared memory.  Columns >= jn resolve to a valid
                 // record of nuclide 0 (never an out-of-range address, never used with conc != 0).
                 __syncwarp();
+                // Short chunks (small materials, the tail of fuel) pack several lookups into one
+                // load instruction: COLS = 4 / 8 / 16 columns x 8 / 4 / 2 lookups per warp-load.
+                auto stage_packed = [&](auto shift_tag) {
+                    constexpr int kShift = decltype(shift_tag)::value;
+                    constexpr int kCols = 1 << kShift, kRows = 32 >> kShift;
+                    const int colj = lane & (kCols - 1), sub = lane >> kShift;
+                    const int nuc_l = colj < jn ? nucs[colj] : 0;
+                    const int *col = P.index_grid + nuc_l;
+                    const uint32_t base_l = (uint32_t)nuc_l * (uint32_t)P.n_gp;
+#pragma unroll
+                    for (int k = 0; k < kSortedGroup / kRows; k++) {
+                        const int i = k * kRows + sub;                       // lookup of the group
+                        const int owner = i / kPerLane, w = i % kPerLane;
+                        uint32_t w_i = 0;
+#pragma unroll
+                        for (int ww = 0; ww < kPerLane; ww++) {
+                            const uint32_t cand = __shfl_sync(kFullMask, where32[ww], owner);
+                            if (ww == w) w_i = cand;
+                        }
+                        const uint32_t no = base_l + (uint32_t)ldg_index_stream(col + (size_t)w_i * (uint32_t)P.n_iso);
+                        warp_rec[owner * kLaneWords + w * 32 + colj] = no;
+                        if (XS_SORTED_STAGE_PF && (i == 0 || i == kSortedGroup - 1)) prefetch_l2(P.pairs + 8 * (size_t)no);
+                    }
+                };
+                if (jn <= 4)       stage_packed(std::integral_constant<int, 2>());
+                else if (jn <= 8)  stage_packed(std::integral_constant<int, 3>());
+                else if (jn <= 16) stage_packed(std::integral_constant<int, 4>());
+                else {
                 const int nuc_l = lane < jn ? nucs[lane] : 0;
                 const int *col = P.index_grid + nuc_l;
                 const uint32_t base_l = (uint32_t)nuc_l * (uint32_t)P.n_gp;
@@ -841,6 +870,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                         if (XS_SORTED_STAGE_PF && ((l == 0 && w == 0) || (l == 31 && w == kPerLane - 1)))
                             prefetch_l2(P.pairs + 8 * (size_t)no);
                     }
+                }
                 }
                 __syncwarp();
                 if (c0 + 32 < n_nuc) {
