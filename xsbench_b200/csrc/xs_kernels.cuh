@@ -708,7 +708,12 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 constexpr int kPerLane = XS_SORTED_PER_LANE;
 XS_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 constexpr int kSortedGroup = 32 * kPerLane;        // lookups per warp-group
-constexpr int kLaneWords = 32 * kPerLane + 1;      // staged record numbers of one lane: [which][step] + pad (bank = lane + step)
+#ifndef XS_SORTED_CHUNK
+#define XS_SORTED_CHUNK 32
+#endif
+constexpr int kChunk = XS_SORTED_CHUNK;            // nuclides (steps) staged at a time: 32, 16 or 8
+constexpr int kChunkShift = kChunk == 32 ? 5 : kChunk == 16 ? 4 : 3;
+constexpr int kLaneWords = kChunk * kPerLane + 1;  // staged record numbers of one lane: [which][step] + pad (bank = lane + step)
 
 #ifndef XS_SORTED_STAGE_UNROLL
 #define XS_SORTED_STAGE_UNROLL 32
@@ -782,9 +787,9 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned int my_sum = 0;
     uint32_t *warp_rec = s_rec + (kStaged ? warp * 32 * kLaneWords : 0);
-    const uint32_t *my_rec = warp_rec + lane * kLaneWords;   // [which * 32 + step]
+    const uint32_t *my_rec = warp_rec + lane * kLaneWords;   // [which * kChunk + step]
     const uint32_t *first_rec = warp_rec;                                        // lookup 0 of the group
-    const uint32_t *last_rec = warp_rec + 31 * kLaneWords + (kPerLane - 1) * 32;  // its last lookup
+    const uint32_t *last_rec = warp_rec + 31 * kLaneWords + (kPerLane - 1) * kChunk;  // its last lookup
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + (kStaged ? warp * kRingBytes : 0);
 
     // a block takes 8 consecutive groups: neighbouring energies share records in L1
@@ -817,8 +822,8 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 #pragma unroll
             for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
 
-        for (int c0 = 0; c0 < n_nuc; c0 += 32) {
-            const int jn = min(32, n_nuc - c0);
+        for (int c0 = 0; c0 < n_nuc; c0 += kChunk) {
+            const int jn = min(kChunk, n_nuc - c0);
             const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
             const int *nucs = s_nuc + S.first + c0;
             if constexpr (kStaged) {
@@ -846,14 +851,14 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                             if (ww == w) w_i = cand;
                         }
                         const uint32_t no = base_l + (uint32_t)ldg_index_stream(col + (size_t)w_i * (uint32_t)P.n_iso);
-                        warp_rec[owner * kLaneWords + w * 32 + colj] = no;
+                        warp_rec[owner * kLaneWords + w * kChunk + colj] = no;
                         if (XS_SORTED_STAGE_PF && (i == 0 || i == kSortedGroup - 1)) prefetch_l2(P.pairs + 8 * (size_t)no);
                     }
                 };
-                if (jn <= 4)       stage_packed(std::integral_constant<int, 2>());
-                else if (jn <= 8)  stage_packed(std::integral_constant<int, 3>());
-                else if (jn <= 16) stage_packed(std::integral_constant<int, 4>());
-                else {
+                if (jn <= 4)                      stage_packed(std::integral_constant<int, 2>());
+                else if (jn <= 8)                 stage_packed(std::integral_constant<int, 3>());
+                else if (jn <= 16 || kChunk < 32) stage_packed(std::integral_constant<int, (kChunkShift < 4 ? kChunkShift : 4)>());
+                else if constexpr (kChunk == 32) {
                 const int nuc_l = lane < jn ? nucs[lane] : 0;
                 const int *col = P.index_grid + nuc_l;
                 const uint32_t base_l = (uint32_t)nuc_l * (uint32_t)P.n_gp;
@@ -863,7 +868,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     for (int w = 0; w < kPerLane; w++) {
                         const uint32_t w_i = __shfl_sync(kFullMask, where32[w], l);
                         const uint32_t no = base_l + (uint32_t)ldg_index_stream(col + (size_t)w_i * (uint32_t)P.n_iso);
-                        warp_rec[l * kLaneWords + w * 32 + lane] = no;
+                        warp_rec[l * kLaneWords + w * kChunk + lane] = no;
                         // A record is used by ~one block only (neighbouring energies), so its first
                         // touch comes from DRAM: request the records of the group's first and last
                         // lookup (the others lie in between) for all 32 steps at once, now.
@@ -873,13 +878,13 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 }
                 }
                 __syncwarp();
-                if (c0 + 32 < n_nuc) {
+                if (c0 + kChunk < n_nuc) {
                     // index-row segments of the next chunk: start their trip from DRAM now
-                    const int last_col = min(63, n_nuc - c0 - 1);
+                    const int last_col = min(2 * kChunk - 1, n_nuc - c0 - 1);
 #pragma unroll
                     for (int w = 0; w < kPerLane; w++) {
                         const int *row = P.index_grid + (size_t)where32[w] * (uint32_t)P.n_iso;
-                        prefetch_l2(row + nucs[32]);
+                        prefetch_l2(row + nucs[kChunk]);
                         prefetch_l2(row + nucs[last_col]);
                     }
                 }
@@ -914,7 +919,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                         uint32_t have = 0xffffffffu;
 #pragma unroll
                         for (int w = 0; w < kPerLane; w++) {
-                            const uint32_t no = my_rec[w * 32 + step];
+                            const uint32_t no = my_rec[w * kChunk + step];
                             if (no != have) {
                                 if (no == no_first)     r = lds_record(slot);
                                 else if (no == no_last) r = lds_record(slot + 128);
