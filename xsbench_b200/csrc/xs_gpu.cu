@@ -287,8 +287,10 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         P.nuc_buckets = (int)nb;
     }
     // pair records (B200 layout for the windowed sweep): one 128-byte line per (nuclide, k)
-    const size_t pair_bytes = (size_t)n_points * 8 * sizeof(double2);
+    // (+ kSpan records of padding: the sorted kernel copies kSpan consecutive records at a time)
+    const size_t pair_bytes = ((size_t)n_points + xs::kSpan) * 8 * sizeof(double2);
     CUDA_TRY(cudaMalloc(&d.pairs, pair_bytes));
+    CUDA_TRY(cudaMemsetAsync(d.pairs + (size_t)n_points * 8, 0, (size_t)xs::kSpan * 8 * sizeof(double2), d.stream));
     xs::xs_build_pairs_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(d.grid, n_iso, n_gp, d.pairs);
     CUDA_TRY(cudaGetLastError());
     d.resident_bytes += pair_bytes;

@@ -723,7 +723,12 @@ constexpr int kLaneWords = kChunk * kPerLane + 1;  // staged record numbers of o
 #endif
 constexpr int kStageUnroll = XS_SORTED_STAGE_UNROLL;   // lookups (x kPerLane index loads) in flight while staging a chunk
 constexpr int kRing = XS_SORTED_RING;              // steps of records in flight per warp (cp.async ring in shared memory)
-constexpr int kRingBytes = kRing * 2 * 128;        // per warp: [step % kRing][first | last lookup's record][128 B]
+#ifndef XS_SORTED_SPAN
+#define XS_SORTED_SPAN 2
+#endif
+constexpr int kSpan = XS_SORTED_SPAN;              // consecutive records per nuclide held in the ring (2, 4 or 8)
+constexpr int kSlotBytes = kSpan * 128;
+constexpr int kRingBytes = kRing * kSlotBytes;     // per warp: [step % kRing][record of the group's first lookup + 0..kSpan-1][128 B]
 
 struct PairRecord { double hi[5], dlt[5], hi_e, d, inv, pad; };
 
@@ -789,7 +794,6 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     uint32_t *warp_rec = s_rec + (kStaged ? warp * 32 * kLaneWords : 0);
     const uint32_t *my_rec = warp_rec + lane * kLaneWords;   // [which * kChunk + step]
     const uint32_t *first_rec = warp_rec;                                        // lookup 0 of the group
-    const uint32_t *last_rec = warp_rec + 31 * kLaneWords + (kPerLane - 1) * kChunk;  // its last lookup
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + (kStaged ? warp * kRingBytes : 0);
 
     // a block takes 8 consecutive groups: neighbouring energies share records in L1
@@ -889,18 +893,26 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     }
                 }
 
-                // ---- gather through the ring: the records of the group's first and last lookup
-                // are copied to shared memory kRing steps ahead (cp.async, 16 lanes x 16 B per
-                // step, two steps per instruction) and read back as broadcasts; a lookup whose
-                // record is neither (possible only when the group spans > 2 grid intervals of
-                // a nuclide) loads it directly.
+                // ---- gather through the ring: kSpan consecutive records per nuclide, starting at
+                // the group's first lookup's, are copied to shared memory kRing steps ahead
+                // (cp.async, 16 B per lane) and read back as broadcasts; a lookup further ahead
+                // than that (a group spanning more than kSpan grid intervals of a nuclide: sparse
+                // materials, XL grids) loads its record directly.
                 auto issue = [&](int s) {                    // steps s, s+1 (s even)
-                    const int step = s + (lane >> 4);
-                    if (step < n_steps) {
-                        const int which = (lane >> 3) & 1;
-                        const uint32_t no = which ? last_rec[step] : first_rec[step];
-                        cp_async_16(ring + (uint32_t)((step % kRing) * 256 + which * 128 + (lane & 7) * 16),
-                                    P.pairs + 8 * (size_t)no + (lane & 7));
+                    // The lookups of a group are sorted, so the records they need of one nuclide
+                    // are CONSECUTIVE: copy kSpan of them starting at the first lookup's.
+                    constexpr int kLanesPerStep = 8 * kSpan;                 // 16-byte pieces of a slot
+                    constexpr int kStepsPerInstr = kLanesPerStep >= 32 ? 1 : 32 / kLanesPerStep;
+#pragma unroll
+                    for (int q = 0; q < 2 / kStepsPerInstr; q++) {
+#pragma unroll
+                        for (int part = 0; part < (kLanesPerStep + 31) / 32; part++) {
+                            const int step = s + q * kStepsPerInstr + (kStepsPerInstr == 2 ? lane >> 4 : 0);
+                            const int piece = part * 32 + (kStepsPerInstr == 2 ? lane & 15 : lane);
+                            if (step < n_steps)
+                                cp_async_16(ring + (uint32_t)((step % kRing) * kSlotBytes + piece * 16),
+                                            P.pairs + 8 * (size_t)first_rec[step] + piece);
+                        }
                     }
                     cp_async_commit();
                 };
@@ -913,17 +925,17 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     for (int h = 0; h < 2; h++) {
                         const int step = j + h;
                         const double conc = c_conc_pad[ci + c0 + step];
-                        const uint32_t no_first = first_rec[step], no_last = last_rec[step];
-                        const uint32_t slot = ring + (uint32_t)((step % kRing) * 256);
+                        const uint32_t no_first = first_rec[step];
+                        const uint32_t slot = ring + (uint32_t)((step % kRing) * kSlotBytes);
                         PairRecord r;
                         uint32_t have = 0xffffffffu;
 #pragma unroll
                         for (int w = 0; w < kPerLane; w++) {
                             const uint32_t no = my_rec[w * kChunk + step];
                             if (no != have) {
-                                if (no == no_first)     r = lds_record(slot);
-                                else if (no == no_last) r = lds_record(slot + 128);
-                                else                    r = ldg_record(P.pairs + 8 * (size_t)no);
+                                const uint32_t ahead = no - no_first;        // 0, 1, ... in a sorted group
+                                if (ahead < (uint32_t)kSpan) r = lds_record(slot + ahead * 128);
+                                else                         r = ldg_record(P.pairs + 8 * (size_t)no);
                                 have = no;
                             }
                             record_step(r, e[w], conc, acc[w]);
