@@ -1,12 +1,17 @@
 // xs_kernels.cuh -- the lookup kernels.
 //
-// Two families (dispatch in xs_gpu.cu):
+// Three families (dispatch in xs_gpu.cu):
 //
-//  * SWEEP pipeline (-k 4/5/6, xs_gpu_lookup_samples, history mode) -- the fast path:
-//      xs_sample_kernel / xs_locate_kernel / xs_history_step_kernel   energy, material, UEG row, histogram
-//      xs_partition_kernel (or radix sort + xs_gather_kernel)         group the lookups by material
-//      xs_window_kernel                                               per material and nuclide window:
-//                                                                     pair records from L2, 4 lanes per lookup
+//  * SORTED pipeline (-k 6, xs_gpu_lookup_samples) -- the fastest path, the bench headline:
+//      xs_sample_kernel / xs_locate_kernel        energy, material, UEG row, sort key, histogram
+//      radix sort (xs_sort.cuh)                   order by (material, energy)
+//      xs_sorted_kernel                           lane per lookup; the lookups of a warp share their
+//                                                 pair records (shared-memory ring, LDS broadcasts)
+//  * SWEEP pipeline (-k 4/5, history mode) -- lookups grouped by material only:
+//      xs_sample_kernel / xs_history_step_kernel  energy, material, UEG row, histogram
+//      xs_partition_kernel                        group the lookups by material
+//      xs_window_kernel                           per material and nuclide window:
+//                                                 pair records from L2, 4 lanes per lookup
 //  * IN-ORDER kernel (-k 0..3, xs_gpu_dump): xs_event_kernel -- one kernel body; what changes
 //    between variants is where a warp's batch of 32 lookups comes from (sampled in-kernel
 //    from the lookup id, or read from sample arrays, optionally through a material filter).
