@@ -1,5 +1,3 @@
 #!/bin/bash
 set -u
-timeout 180 python scripts/quick_bench.py --kernels 6 --reps 3 2>&1 | tail -1
-KERNELS=6 timeout 180 bash scripts/gpu_variants.sh notma
-timeout 900 python -m pytest tests -x -q -m "gpu and not slow" 2>&1 | tail -3
+for v in p4c16 p4c8; do echo "== $v"; XSB200_GPU_LIB=$PWD/xsbench_b200/variants/libxsb200_$v.so python scripts/exp/split_by_material.py 2>&1 | head -4; done
