@@ -407,3 +407,25 @@ def test_official_large_event_full_size():
         assert gpu.run(xs.make_inputs(size="large", method="history")).checksum == 954318
     finally:
         gpu.release()
+
+
+@pytest.mark.gpu
+@pytest.mark.slow
+def test_billion_lookups_bounded_passes():
+    """BASELINE config 5: 10^9 lookups worked through in bounded passes (XSB200_MAX_PASS, 2^26 by
+    default) on the device-generated large problem.  Golden: the reference CUDA build's output
+    (260078) corrected for the int overflow of its thrust::reduce(..., 0) at sums above 2^31
+    (cuda/Simulation.cu:34): (260078 + 35965) mod 999983 = 296043."""
+    inp = xs.make_inputs(size="large", method="event", lookups=1_000_000_000, kernel_id=6)
+    mats = xs.materials_only(inp)
+    with xs.move_simulation_data_to_device(inp, mats) as gpu:
+        res = gpu.run(inp)
+        assert res.n_lookups == 1_000_000_000 and res.checksum == 296043
+        assert xs.expected_checksum(inp) == 296043
+        assert res.verification > 2**31
+        k4 = gpu.run(xs.make_inputs(size="large", method="event", lookups=1_000_000_000, kernel_id=4))
+        assert k4.verification == res.verification
+        # any partition of the id range sums to the whole
+        a = gpu.run_range(0, 400_000_000, inp).verification + gpu.run_range(400_000_000, 600_000_000, inp).verification
+        assert a == res.verification
+    xs.free_simulation_data(mats)

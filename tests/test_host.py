@@ -259,6 +259,11 @@ def test_expected_checksum_table():
     assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-s", "small", "-g", "1000", "-l", "100000"])) == 302880
     assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-s", "XL", "-l", "1000000"])) == 3377
     assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-l", "12345"])) is None
+    # 10^9 lookups: the reference CUDA build's printed value corrected for its 32-bit accumulator
+    # (thrust::reduce(..., 0), cuda/Simulation.cu:34): sums above 2^31 lose 2^64 - 2^32
+    wrap = (2**64 - 2**32) % 999983
+    assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-l", "1000000000"])) == (260078 - wrap) % 999983 == 296043
+    assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-s", "XL", "-l", "1000000000"])) == (509518 - wrap) % 999983 == 545483
 
 
 def test_print_results_validity(capfd):
