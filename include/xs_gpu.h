@@ -150,6 +150,11 @@ typedef struct {
  * the timed region: cuda/Simulation.cu:401-409), builds search-acceleration tables and sets
  * the L2 persistence window.  Device used: the calling thread's current CUDA device, then
  * the following ordinals.
+ * A unionized grid that one GPU cannot hold (XXL: 253 GB of index rows) is sharded by energy
+ * band when n_gpus > 1: GPU g holds the index rows of band g, every GPU draws every lookup id
+ * and keeps the lookups of its band; xs_gpu_run adds the bands up (no data exchange).  In that
+ * mode every event variant runs the sorted pipeline; history mode, xs_gpu_lookup_samples and
+ * xs_gpu_dump return XS_ERR_UNSUPP.
  */
 int xs_gpu_init(const Inputs *in, const SimulationData *host_sd, int n_gpus, xs_gpu_ctx **out);
 

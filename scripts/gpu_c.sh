@@ -1,3 +1,3 @@
 #!/bin/bash
 set -u
-timeout 1200 python -m pytest tests -x -q -m "gpu and slow" -k billion 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "energy_bands or all_variants" 2>&1 | tail -8

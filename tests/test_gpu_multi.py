@@ -45,3 +45,29 @@ def test_bench_two_ranks_weak_scaling():
     assert line["n_gpus"] == 2 and line["lookups_counted"] == 2_000_000 and line["scaling"] == "weak"
     want = ol.OracleProblem(68, 11303, 2).event(0, 2_000_000, os.cpu_count() or 1) % 999983
     assert line["checksum"] == want
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_in_process_energy_bands(monkeypatch):
+    """XSB200_BANDS=2 on 2 GPUs: each GPU holds half of the index rows, draws all ids, keeps its band;
+    the NCCL all-reduce adds the two halves up."""
+    monkeypatch.setenv("XSB200_BANDS", "2")
+    inp = xs.make_inputs(size="small", method="event", grid="unionized", lookups=100000, gridpoints=1000, kernel_id=6)
+    for sd in (xs.grid_init_do_not_profile(inp), xs.materials_only(inp)):
+        with xs.move_simulation_data_to_device(inp, sd, n_gpus=2) as gpu:
+            res = gpu.run(inp)
+            assert res.n_gpus == 2 and res.n_lookups == 100000 and res.verification == 302880
+        xs.free_simulation_data(sd)
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_xxl_unionized_across_gpus():
+    """XXL unionized (253 GB of index rows) does not fit one B200: with several GPUs the grid is
+    sharded by energy band automatically.  Golden 344 (the hash is grid-type invariant)."""
+    inp = xs.make_inputs(size="XXL", method="event", grid="unionized", lookups=1_000_000, kernel_id=6)
+    mats = xs.materials_only(inp)
+    with xs.move_simulation_data_to_device(inp, mats, n_gpus=_n_gpus()) as gpu:
+        res = gpu.run(inp)
+        assert res.n_lookups == 1_000_000 and res.checksum == 344
+    xs.free_simulation_data(mats)

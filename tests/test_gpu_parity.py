@@ -252,6 +252,41 @@ def test_sorted_pipeline_variants_agree(monkeypatch, env, grid, hb):
         p.close()
 
 
+# ---- energy-band sharding of the unionized grid (what XXL needs), exercised on one GPU ----------------------
+@pytest.mark.parametrize("device_init", [False, True])
+def test_energy_bands_sum_to_the_whole(monkeypatch, device_init):
+    """Each context holds the index rows of one energy band, draws EVERY lookup id and keeps the ones
+    whose row lies in its band (SURVEY 8e option 2): the per-band sums add up to the full result,
+    whatever -k variant is asked for."""
+    n, bands = 100000, 3
+    total_v = total_n = 0
+    for b in range(bands):
+        monkeypatch.setenv("XSB200_BANDS", str(bands))
+        monkeypatch.setenv("XSB200_BAND_INDEX", str(b))
+        inp = xs.make_inputs(size="small", method="event", grid="unionized", lookups=n, gridpoints=1000, kernel_id=6)
+        sd = xs.materials_only(inp) if device_init else xs.grid_init_do_not_profile(inp)
+        with xs.move_simulation_data_to_device(inp, sd) as gpu:
+            r6 = gpu.run(inp)
+            r0 = gpu.run(xs.make_inputs(size="small", method="event", grid="unionized", lookups=n, gridpoints=1000, kernel_id=0))
+            assert (r0.verification, r0.n_lookups) == (r6.verification, r6.n_lookups)
+            assert 0 < r6.n_lookups < n
+            # the band's index rows are the corresponding rows of the full grid
+            if not device_init:
+                info = gpu.info()
+                n_ueg = info.n_isotopes * info.n_gridpoints
+                r_lo, r_hi = n_ueg * b // bands, n_ueg * (b + 1) // bands
+                rows = np.empty((r_hi - r_lo) * info.n_isotopes, np.int32)
+                gpu._check(gpu._lib.xs_gpu_read_array(gpu._ctx, 2, r_lo * info.n_isotopes * 4, rows.nbytes, rows.ctypes.data))
+                full = xs.simulation_arrays(inp, sd)["index_grid"]
+                assert np.array_equal(rows, full[r_lo * info.n_isotopes:r_hi * info.n_isotopes])
+            with pytest.raises(xs.XSGpuError):
+                gpu.run(xs.make_inputs(size="small", method="history", grid="unionized", gridpoints=1000, particles=100, lookups=5))
+            total_v += r6.verification
+            total_n += r6.n_lookups
+        xs.free_simulation_data(sd)
+    assert total_n == n and total_v == 302880
+
+
 # ---- device-side generator: byte-identical to the host generator --------------------------------------------
 @pytest.mark.parametrize("size,n_gp,grid,hb", [("small", 1000, "unionized", 10000), ("small", 1000, "hash", 500),
                                                ("small", 1000, "nuclide", 10000), ("large", 300, "unionized", 10000),

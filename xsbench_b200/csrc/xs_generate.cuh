@@ -92,11 +92,13 @@ gen_check_duplicates_kernel(const double2 *grid, long n_iso, long n_gp, int *dup
 // Block = one tile of kIndexTileRows rows; warp w handles nuclides [32w', 32w'+32) in turn.
 constexpr int kIndexTileRows = 512;
 __global__ void __launch_bounds__(256)
-gen_index_kernel(const double *ueg, const double2 *grid, long n_iso, long n_gp, int *index_grid)
+gen_index_kernel(const double *ueg, const double2 *grid, long n_iso, long n_gp, long row_begin, long row_end,
+                 int *index_grid)
 {
-    const long n_rows = n_iso * n_gp;
-    const long e_begin = (long)blockIdx.x * kIndexTileRows;
-    const long e_end = min(e_begin + (long)kIndexTileRows, n_rows);
+    // rows [row_begin, row_end) of the unionized grid (an energy band; the whole grid by default);
+    // index_grid holds exactly those rows
+    const long e_begin = row_begin + (long)blockIdx.x * kIndexTileRows;
+    const long e_end = min(e_begin + (long)kIndexTileRows, row_end);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (long i0 = 32L * warp; i0 < n_iso; i0 += 32L * n_warps) {
         const long i = i0 + lane;
@@ -126,7 +128,7 @@ gen_index_kernel(const double *ueg, const double2 *grid, long n_iso, long n_gp, 
                 cursor++;
                 next_energy = g[3 * (long)(cursor + 1)].x;
             }
-            if (on) index_grid[e * n_iso + i] = cursor;                // 32 consecutive ints per warp
+            if (on) index_grid[(e - row_begin) * n_iso + i] = cursor;    // 32 consecutive ints per warp
         }
     }
 }
@@ -150,7 +152,21 @@ gen_hash_kernel(const double2 *grid, long n_iso, long n_gp, int hash_bins, int *
     }
 }
 
-// Generate grid (+ ueg, index_grid / hash grid) into pre-allocated device arrays.
+// Index rows [row_begin, row_end) of the unionized grid from the generated grid + ueg (phase 2 of the
+// generator; separate so that the sort temporaries of phase 1 are gone before a large index band is
+// allocated).
+inline int generate_index_rows(const double *ueg, const double2 *grid, long n_iso, long n_gp, long row_begin, long row_end,
+                               int *index_grid, cudaStream_t stream)
+{
+    const long rows = row_end - row_begin;
+    if (rows <= 0) return 0;
+    const int tiles = (int)((rows + kIndexTileRows - 1) / kIndexTileRows);
+    gen_index_kernel<<<tiles, 256, 0, stream>>>(ueg, grid, n_iso, n_gp, row_begin, row_end, index_grid);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// Generate grid (+ ueg, hash grid) into pre-allocated device arrays; the unionized index grid is
+// built by generate_index_rows afterwards (index_grid may be null for that grid type).
 // Returns 0, -1 on CUDA/sort failure, -2 if a nuclide holds duplicate energies.
 inline int generate_problem(int grid_type, long n_iso, long n_gp, int hash_bins, double2 *grid, double *ueg,
                             int *index_grid, int sm_count, cudaStream_t stream)
@@ -197,10 +213,7 @@ inline int generate_problem(int grid_type, long n_iso, long n_gp, int hash_bins,
             gen_check_duplicates_kernel<<<blocks, 256, 0, stream>>>(grid, n_iso, n_gp, d_flag);
         }
     }
-    if (rc == 0 && grid_type == kUnionized) {
-        const int tiles = (int)((n_points + kIndexTileRows - 1) / kIndexTileRows);
-        gen_index_kernel<<<tiles, 256, 0, stream>>>(ueg, grid, n_iso, n_gp, index_grid);
-    } else if (rc == 0 && grid_type == kHash) {
+    if (rc == 0 && grid_type == kHash) {
         const long n = (long)hash_bins * n_iso;
         gen_hash_kernel<<<(int)std::min<long>((n + 255) / 256, (long)sm_count * 32), 256, 0, stream>>>(grid, n_iso, n_gp, hash_bins, index_grid);
     }

@@ -36,6 +36,14 @@ int set_error(int code, const char *fmt, ...)
     return code;
 }
 
+// Every entry point leaves the calling thread's current device as it found it (the multi-GPU paths
+// switch devices internally).
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 #define CUDA_TRY(call)                                                                         \
     do {                                                                                       \
         cudaError_t err__ = (call);                                                            \
@@ -70,7 +78,9 @@ struct DeviceState {
     // problem
     unsigned char *hot_slab = nullptr;     // [bucket table | UEG] or hash index: L2-persisting
     size_t hot_bytes = 0;
-    int *index_grid = nullptr;             // unionized index grid (streamed)
+    int *index_grid = nullptr;             // unionized index grid (streamed); in band mode only rows [row0, row1)
+    long row0 = 0, row1 = 0;               // this device's energy band of the unionized grid (whole grid: [0, n_ueg))
+    int band = 0;                          // band index of this device (band mode)
     double2 *grid = nullptr;
     int *mat_first = nullptr, *mat_nuc = nullptr;
     double *mat_conc = nullptr;
@@ -127,6 +137,8 @@ struct xs_gpu_ctx {
     long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
     int bin_bits = 0;                      // -k 6: energy bits of the one-pass bin sort; 0 (default) = three-pass radix sort,
                                            // which measured the same total (5.49 vs 5.56 ms) and keeps a deterministic order
+    int n_bands = 1;                       // > 1: energy-band sharding of the unionized index grid (SURVEY 8e option 2):
+                                           // device g holds rows of band g, samples every lookup id and keeps those in its band
     int fuse_gather = 1;                   // -k 6: the lookup kernel reads its samples through the sort's permutation
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
@@ -241,11 +253,15 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
         bucket = reinterpret_cast<uint32_t *>(d.hot_slab);
         ueg = reinterpret_cast<double *>(d.hot_slab + bucket_bytes);
-        const size_t index_bytes = (size_t)n_ueg * (size_t)n_iso * sizeof(int);
-        CUDA_TRY(cudaMalloc(&d.index_grid, index_bytes));
+        d.row0 = n_ueg * d.band / ctx->n_bands;
+        d.row1 = n_ueg * (d.band + 1) / ctx->n_bands;
+        const size_t index_bytes = (size_t)(d.row1 - d.row0) * (size_t)n_iso * sizeof(int);
         if (!generate) {
+            // (band mode never copies from a peer: every device holds different rows)
+            CUDA_TRY(cudaMalloc(&d.index_grid, index_bytes));
             CUDA_TRY(copy_in(ueg, sd->unionized_energy_array, peer ? peer->hot_slab + bucket_bytes : nullptr, ueg_bytes));
-            CUDA_TRY(copy_in(d.index_grid, sd->index_grid, peer ? peer->index_grid : nullptr, index_bytes));
+            CUDA_TRY(copy_in(d.index_grid, sd->index_grid ? sd->index_grid + d.row0 * n_iso : nullptr,
+                             peer ? peer->index_grid : nullptr, index_bytes));
         }
         d.resident_bytes += d.hot_bytes + index_bytes;
         P.ueg = ueg;
@@ -253,7 +269,6 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         P.n_ueg = n_ueg;
         P.n_buckets = (int)n_buckets;
         P.bucket_scale = (double)n_buckets;
-        P.index_grid = d.index_grid;
     } else if (ctx->grid_type == XS_HASH) {
         d.hot_bytes = (size_t)in->hash_bins * (size_t)n_iso * sizeof(int);
         CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
@@ -262,13 +277,21 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         P.index_grid = reinterpret_cast<const int *>(d.hot_slab);
     }
     if (generate) {
-        int *index_dst = ctx->grid_type == XS_UNIONIZED ? d.index_grid : reinterpret_cast<int *>(d.hot_slab);
-        const int g = xs::generate_problem(ctx->grid_type, n_iso, n_gp, in->hash_bins, d.grid, ueg, index_dst, d.sm_count, d.stream);
+        int *index_dst = ctx->grid_type == XS_UNIONIZED ? nullptr : reinterpret_cast<int *>(d.hot_slab);
+        int g = xs::generate_problem(ctx->grid_type, n_iso, n_gp, in->hash_bins, d.grid, ueg, index_dst, d.sm_count, d.stream);
         if (g == -2)
             return set_error(XS_ERR_UNSUPP, "device generator: a nuclide holds two equal energies; generate on the host instead");
+        if (g == 0 && ctx->grid_type == XS_UNIONIZED) {
+            // the generator's sort temporaries are gone: now the (possibly very large) index rows
+            const size_t index_bytes = (size_t)(d.row1 - d.row0) * (size_t)n_iso * sizeof(int);
+            CUDA_TRY(cudaMalloc(&d.index_grid, index_bytes));
+            g = xs::generate_index_rows(ueg, d.grid, n_iso, n_gp, d.row0, d.row1, d.index_grid, d.stream);
+        }
         if (g != 0)
             return set_error(XS_ERR_CUDA, "device generator failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    // kernels index the grid by global row number: bias the pointer by the band's first row
+    if (ctx->grid_type == XS_UNIONIZED) P.index_grid = d.index_grid - d.row0 * n_iso;
     if (ctx->grid_type == XS_UNIONIZED) {
         xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(ueg, n_points, (double)n_buckets, (int)n_buckets, bucket);
         CUDA_TRY(cudaGetLastError());
@@ -574,7 +597,9 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
                                                        with_where ? d.samp_where : nullptr,
                                                        with_key ? d.key[0] : nullptr,
                                                        with_hist ? d.histogram : nullptr,
-                                                       with_bins ? d.bin_count : nullptr, 28 - ctx->bin_bits);
+                                                       with_bins ? d.bin_count : nullptr, 28 - ctx->bin_bits,
+                                                       ctx->n_bands > 1 ? (uint32_t)d.row0 : 0u,
+                                                       ctx->n_bands > 1 ? (uint32_t)d.row1 : 0xffffffffu);
     d.bins_ready = with_bins;
     CUDA_TRY(cudaGetLastError());
     d.launches++;
@@ -718,8 +743,13 @@ int enqueue_event_all(xs_gpu_ctx *ctx, int kernel_id, long first_id, long count)
     long most = 0;
     for (int g = 0; g < n; g++) {
         DeviceState &d = ctx->dev[g];
-        lo[g] = first_id + count * g / n;
-        cnt[g] = first_id + count * (g + 1) / n - lo[g];
+        if (ctx->n_bands > 1) {          // band mode: every device draws every id, keeps its band
+            lo[g] = first_id;
+            cnt[g] = count;
+        } else {
+            lo[g] = first_id + count * g / n;
+            cnt[g] = first_id + count * (g + 1) / n - lo[g];
+        }
         done[g] = 0;
         most = std::max(most, cnt[g]);
         CUDA_TRY(cudaSetDevice(d.device));
@@ -977,6 +1007,36 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->dev.resize(n_gpus);
     for (int g = 0; g < n_gpus; g++) ctx->dev[g].device = dev0 + g;
 
+    // Energy-band sharding of the unionized index grid (SURVEY 8e option 2).  XSB200_BANDS=N forces
+    // it; by default it switches on when several GPUs are given and one GPU cannot hold the grid
+    // (XXL: 253 GB of index rows).  A single-GPU context can hold one band (XSB200_BAND_INDEX): the
+    // caller then sums the results of the N contexts, e.g. one rank per GPU.
+    if (in->grid_type == XS_UNIONIZED) {
+        const int forced = env_int("XSB200_BANDS", 0);
+        if (forced > 1) {
+            ctx->n_bands = forced;
+        } else if (forced == 0 && n_gpus > 1) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const double points = (double)in->n_isotopes * (double)in->n_gridpoints;
+            const double need = points * (double)in->n_isotopes * 4.0 + points * (48.0 + 128.0 + 8.0 + 40.0);
+            if (need > 0.92 * (double)total_b) ctx->n_bands = n_gpus;
+        }
+        if (ctx->n_bands > 1) {
+            const int index = env_int("XSB200_BAND_INDEX", -1);
+            if (n_gpus > 1 && ctx->n_bands != n_gpus) {
+                delete ctx;
+                return set_error(XS_ERR_ARG, "xs_gpu_init: %d energy bands need %d GPUs (got %d)", forced, forced, n_gpus);
+            }
+            if (n_gpus == 1 && (index < 0 || index >= ctx->n_bands)) {
+                delete ctx;
+                return set_error(XS_ERR_ARG, "xs_gpu_init: XSB200_BANDS=%d on one GPU needs XSB200_BAND_INDEX in [0, %d)", forced, forced);
+            }
+            for (int g = 0; g < n_gpus; g++) ctx->dev[g].band = n_gpus > 1 ? g : index;
+            ctx->bin_bits = 0;            // (the bin sort has no bin for dropped lookups)
+        }
+    }
+
     int rc = XS_OK;
     for (int g = 0; g < n_gpus && rc == XS_OK; g++) {
         if (g > 0) {
@@ -990,13 +1050,14 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
                 cudaGetLastError();
             }
         }
-        rc = upload_device(ctx, ctx->dev[g], in, sd, g > 0 ? &ctx->dev[0] : nullptr);
+        rc = upload_device(ctx, ctx->dev[g], in, sd, g > 0 && ctx->n_bands == 1 ? &ctx->dev[0] : nullptr);
     }
     if (rc == XS_OK && in->simulation_method == XS_EVENT_BASED && in->kernel_id != 0 && in->lookups > 0) {
         // pre-allocate the sample / sort buffers here, not inside the timed region
-        const long per_gpu = ((long)in->lookups + n_gpus - 1) / n_gpus;
+        const long per_gpu = ctx->n_bands > 1 ? (long)in->lookups : ((long)in->lookups + n_gpus - 1) / n_gpus;
         for (int g = 0; g < n_gpus && rc == XS_OK; g++)
-            rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4, ctx->bin_bits);
+            rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4 || ctx->n_bands > 1,
+                                       ctx->bin_bits);
     }
     if (rc == XS_OK && n_gpus > 1) rc = xs_multi_init(ctx);
     if (rc != XS_OK) {
@@ -1013,6 +1074,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
 
 int xs_gpu_run_range(xs_gpu_ctx *ctx, const Inputs *in, long first_id, long count, xs_gpu_result *res)
 {
+    DeviceGuard restore_device;
     if (!ctx || !in || !res) return set_error(XS_ERR_ARG, "xs_gpu_run: NULL argument");
     if (count < 0 || first_id < 0) return set_error(XS_ERR_ARG, "xs_gpu_run: negative range");
     const bool event = in->simulation_method == XS_EVENT_BASED;
@@ -1026,10 +1088,15 @@ int xs_gpu_run_range(xs_gpu_ctx *ctx, const Inputs *in, long first_id, long coun
     if (in->grid_type != ctx->grid_type || in->n_isotopes != ctx->n_iso || in->n_gridpoints != ctx->n_gp)
         return set_error(XS_ERR_ARG, "xs_gpu_run: Inputs do not match the problem uploaded by xs_gpu_init");
 
+    if (ctx->n_bands > 1 && !event)
+        return set_error(XS_ERR_UNSUPP, "xs_gpu_run: history mode is not available on an energy-band-sharded grid");
+
     const double t0 = wall_seconds();
     const int n = (int)ctx->dev.size();
     if (event) {
-        int rc = enqueue_event_all(ctx, in->kernel_id, first_id, count);
+        // band mode: every variant runs the sorted pipeline (the only one that can drop the
+        // lookups of other bands)
+        int rc = enqueue_event_all(ctx, ctx->n_bands > 1 ? 6 : in->kernel_id, first_id, count);
         if (rc != XS_OK) return rc;
     } else {
         for (int g = 0; g < n; g++) {
@@ -1051,8 +1118,11 @@ int xs_gpu_run(xs_gpu_ctx *ctx, const Inputs *in, xs_gpu_result *res)
 int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_mat, long n,
                           double *h_macro_xs_out, xs_gpu_result *res)
 {
+    DeviceGuard restore_device;
     if (!ctx || !h_energy || !h_mat || !res || n < 0)
         return set_error(XS_ERR_ARG, "xs_gpu_lookup_samples: bad argument");
+    if (ctx->n_bands > 1)
+        return set_error(XS_ERR_UNSUPP, "xs_gpu_lookup_samples: not available on an energy-band-sharded grid");
     const double t0 = wall_seconds();
     const int ng = (int)ctx->dev.size();
     for (int g = 0; g < ng; g++) {
@@ -1125,7 +1195,9 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
 int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, int *h_mat_out,
                 double *h_macro_xs_out, int *h_argmax_out)
 {
+    DeviceGuard restore_device;
     if (!ctx || n < 0 || first_id < 0) return set_error(XS_ERR_ARG, "xs_gpu_dump: bad argument");
+    if (ctx->n_bands > 1) return set_error(XS_ERR_UNSUPP, "xs_gpu_dump: not available on an energy-band-sharded grid");
     if (n == 0) return XS_OK;
     DeviceState &d = ctx->dev[0];
     CUDA_TRY(cudaSetDevice(d.device));
@@ -1156,6 +1228,7 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
 
 int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit, int hi_bit, uint32_t *h_perm_out)
 {
+    DeviceGuard restore_device;
     if (!ctx || !h_keys || !h_perm_out || n < 0 || lo_bit < 0 || hi_bit > 32 || lo_bit >= hi_bit)
         return set_error(XS_ERR_ARG, "xs_gpu_sort_keys: bad argument");
     if (n == 0) return XS_OK;
@@ -1176,6 +1249,7 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
 
 int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_bytes, void *h_dst)
 {
+    DeviceGuard restore_device;
     if (!ctx || !h_dst || offset_bytes < 0 || n_bytes < 0) return set_error(XS_ERR_ARG, "xs_gpu_read_array: bad argument");
     DeviceState &d = ctx->dev[0];
     const long n_points = ctx->n_iso * ctx->n_gp;
@@ -1187,6 +1261,8 @@ int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_byte
     } else if (which == XS_ARRAY_INDEX_GRID && ctx->grid_type != XS_NUCLIDE) {
         src = reinterpret_cast<const unsigned char *>(d.P.index_grid);
         total = (ctx->grid_type == XS_UNIONIZED ? n_points : (long)ctx->hash_bins) * ctx->n_iso * 4;
+        if (ctx->n_bands > 1 && (offset_bytes < d.row0 * ctx->n_iso * 4 || offset_bytes + n_bytes > d.row1 * ctx->n_iso * 4))
+            return set_error(XS_ERR_ARG, "xs_gpu_read_array: GPU 0 holds index rows [%ld, %ld) only (energy-band sharding)", d.row0, d.row1);
     } else return set_error(XS_ERR_ARG, "xs_gpu_read_array: array %d does not exist for this grid type", which);
     if (offset_bytes + n_bytes > total) return set_error(XS_ERR_ARG, "xs_gpu_read_array: range beyond the array (%ld bytes)", total);
     CUDA_TRY(cudaSetDevice(d.device));
@@ -1226,6 +1302,7 @@ int xs_gpu_get_info(const xs_gpu_ctx *ctx, xs_gpu_info *info)
 
 int xs_gpu_finalize(xs_gpu_ctx *ctx)
 {
+    DeviceGuard restore_device;
     if (!ctx) return XS_OK;
     xs_multi_destroy(ctx);
     for (DeviceState &d : ctx->dev) {

@@ -1068,7 +1068,8 @@ __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, double *energy, int *mat,
-                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, unsigned int *bin_count, int bin_shift)
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, unsigned int *bin_count, int bin_shift,
+                 uint32_t row_begin, uint32_t row_end)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -1085,11 +1086,19 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
             const double e = lcg_to_double(s1);
             energy[t] = e;
             mat[t] = m;
-            if (where) where[t] = (uint32_t)locate_rt(P, grid_type, e);
-            const uint32_t k32 = ((uint32_t)m << 28) | (uint32_t)(s1 >> 35);
+            bool mine = true;
+            if (where) {
+                // energy-band sharding (unionized grid too large for one GPU): every device draws
+                // every lookup and keeps those whose row lies in its band [row_begin, row_end);
+                // the others get material 15 in the key (sorted to the end, never looked up)
+                const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
+                where[t] = w;
+                mine = w >= row_begin && w < row_end;
+            }
+            const uint32_t k32 = ((mine ? (uint32_t)m : 15u) << 28) | (uint32_t)(s1 >> 35);
             if (key) key[t] = k32;
             if (bin_count) atomicAdd(bin_count + (k32 >> bin_shift), 1u);
-            if (mat_histogram) atomicAdd(&s_hist[m], 1u);
+            if (mat_histogram && mine) atomicAdd(&s_hist[m], 1u);
             s = apply(hop, s);
         }
     }
