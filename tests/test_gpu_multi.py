@@ -70,4 +70,8 @@ def test_xxl_unionized_across_gpus():
     with xs.move_simulation_data_to_device(inp, mats, n_gpus=_n_gpus()) as gpu:
         res = gpu.run(inp)
         assert res.n_lookups == 1_000_000 and res.checksum == 344
+        # default lookup count: 33803, pinned by the CPU oracle on the XXL nuclide grid (the hash does
+        # not depend on the grid type)
+        res = gpu.run(xs.make_inputs(size="XXL", method="event", grid="unionized", kernel_id=6))
+        assert res.n_lookups == 17_000_000 and res.checksum == 33803
     xs.free_simulation_data(mats)

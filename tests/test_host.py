@@ -258,6 +258,7 @@ def test_expected_checksum_table():
     assert xs.expected_checksum(xs.read_CLI([])) == 954318
     assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-s", "small", "-g", "1000", "-l", "100000"])) == 302880
     assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-s", "XL", "-l", "1000000"])) == 3377
+    assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-s", "XXL"])) == 33803
     assert xs.expected_checksum(xs.read_CLI(["-m", "event", "-l", "12345"])) is None
     # 10^9 lookups: the reference CUDA build's printed value corrected for its 32-bit accumulator
     # (thrust::reduce(..., 0), cuda/Simulation.cu:34): sums above 2^31 lose 2^64 - 2^32
