@@ -31,6 +31,8 @@ struct MultiState {
     const char *(*GetErrorString)(xs_ncclResult_t) = nullptr;
 };
 
+int xs_multi_allreduce(xs_gpu_ctx *ctx);
+
 int xs_multi_init(xs_gpu_ctx *ctx)
 {
     MultiState *m = new MultiState;
@@ -54,7 +56,14 @@ int xs_multi_init(xs_gpu_ctx *ctx)
         m->n = 0;
         return set_error(XS_ERR_NCCL, "ncclCommInitAll failed: %s", m->GetErrorString ? m->GetErrorString(r) : "?");
     }
-    return XS_OK;
+    // the first collective sets up channels and buffers (~60 ms): do it here, not in the first run
+    int rc = xs_multi_allreduce(ctx);
+    for (int g = 0; g < m->n && rc == XS_OK; g++) {
+        DeviceState &d = ctx->dev[g];
+        if (cudaSetDevice(d.device) != cudaSuccess || cudaStreamSynchronize(d.stream) != cudaSuccess)
+            rc = set_error(XS_ERR_CUDA, "NCCL warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return rc;
 }
 
 int xs_multi_allreduce(xs_gpu_ctx *ctx)
