@@ -1059,6 +1059,11 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
             rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4 || ctx->n_bands > 1,
                                        ctx->bin_bits);
     }
+    if (rc == XS_OK && in->simulation_method == XS_HISTORY_BASED && in->particles > 0 && ctx->sweep && ctx->n_bands == 1) {
+        // history mode works on one generation (= all particles) at a time
+        const long per_gpu = ((long)in->particles + n_gpus - 1) / n_gpus;
+        for (int g = 0; g < n_gpus && rc == XS_OK; g++) rc = ensure_sample_buffers(ctx->dev[g], per_gpu, true);
+    }
     if (rc == XS_OK && n_gpus > 1) rc = xs_multi_init(ctx);
     if (rc != XS_OK) {
         char keep[sizeof g_error];
