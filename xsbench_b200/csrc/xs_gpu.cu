@@ -104,6 +104,7 @@ struct DeviceState {
     double2 *pairs = nullptr;              // pair records for the window kernel (128 B per grid point)
     uint32_t *nuc_bucket = nullptr;        // nuclide-grid mode: per-nuclide search tables
     uint32_t *samp_where = nullptr;        // [sample_capacity] UEG row / hash bin per sample
+    double2 *samp_pack = nullptr;          // [sample_capacity] (energy, row) packed: what the -k 6 kernel reads through the permutation
     double *grp_e = nullptr;               // samples grouped by material: energy,
     uint32_t *grp_where = nullptr;         //   row / bin,
     int *grp_mat = nullptr;                //   material (fuel/other partition only),
@@ -139,6 +140,7 @@ struct xs_gpu_ctx {
                                            // which measured the same total (5.49 vs 5.56 ms) and keeps a deterministic order
     int n_bands = 1;                       // > 1: energy-band sharding of the unionized index grid (SURVEY 8e option 2):
                                            // device g holds rows of band g, samples every lookup id and keeps those in its band
+    int pack_samples = 1;                  // -k 6: samples also stored as 16-byte (energy, row) records for the permuted reads
     int fuse_gather = 1;                   // -k 6: the lookup kernel reads its samples through the sort's permutation
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
@@ -400,10 +402,10 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort, int bin_bits =
     if (n > d.sample_capacity) {
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); d.key[i] = d.perm[i] = nullptr; }
-        cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
+        cudaFree(d.samp_where); cudaFree(d.samp_pack); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
         cudaFree(d.sweep_partial); cudaFree(d.hist_seed); cudaFree(d.hist_fwd);
         d.hist_seed = nullptr; d.hist_fwd = nullptr;
-        d.samp_where = nullptr; d.grp_e = nullptr; d.grp_where = nullptr; d.grp_mat = nullptr; d.grp_id = nullptr;
+        d.samp_where = nullptr; d.samp_pack = nullptr; d.grp_e = nullptr; d.grp_where = nullptr; d.grp_mat = nullptr; d.grp_id = nullptr;
         d.sweep_partial = nullptr;
         d.samp_e = nullptr; d.samp_mat = nullptr;
         CUDA_TRY(cudaMalloc(&d.samp_e, (size_t)n * sizeof(double)));
@@ -417,6 +419,7 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort, int bin_bits =
         }
         const size_t cap = (size_t)d.sample_capacity;
         CUDA_TRY(cudaMalloc(&d.samp_where, cap * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d.samp_pack, cap * sizeof(double2)));
         CUDA_TRY(cudaMalloc(&d.grp_e, cap * sizeof(double)));
         CUDA_TRY(cudaMalloc(&d.grp_where, cap * sizeof(uint32_t)));
         CUDA_TRY(cudaMalloc(&d.grp_mat, cap * sizeof(int)));
@@ -473,6 +476,7 @@ struct GroupedBatch {
     const uint32_t *where;
     const uint32_t *id;            // original sample index per slot (macro_xs dumps)
     bool indirect;                 // energy / where are still in sample order: the kernel reads them through id
+    const double2 *pack;           // indirect mode: packed (energy, row) per sample, or null
     double2 *partial;
     long offset[XS_NUM_MATERIALS]; // first slot of each material (host copy of the histogram prefix)
     long count[XS_NUM_MATERIALS];  // lookups per material
@@ -530,6 +534,7 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
     a.where = b.where;
     a.sample_id = b.id;
     a.indirect = b.indirect;
+    a.pack = b.pack;
     a.first_window = a.last_window = 1;
     WindowKernel k = table[ctx->grid_type];
     int blocks = 0;
@@ -593,16 +598,21 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
     const bool with_bins = with_key && ctx->bin_bits > 0;
     if (with_bins)
         CUDA_TRY(cudaMemsetAsync(d.bin_count, 0, ((size_t)XS_NUM_MATERIALS << ctx->bin_bits) * sizeof(unsigned int), d.stream));
-    xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_id, count, d.samp_e, d.samp_mat,
-                                                       with_where ? d.samp_where : nullptr,
+    // -k 6 on the default path reads its samples only as packed (energy, row) records through the
+    // sort permutation: the separate arrays are not written then
+    const bool pack_only = with_key && ctx->pack_samples && ctx->fuse_gather && ctx->sorted_kernel && !with_bins;
+    xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_id, count,
+                                                       pack_only ? nullptr : d.samp_e, pack_only ? nullptr : d.samp_mat,
+                                                       with_where && !pack_only ? d.samp_where : nullptr,
                                                        with_key ? d.key[0] : nullptr,
                                                        with_hist ? d.histogram : nullptr,
                                                        with_bins ? d.bin_count : nullptr, 28 - ctx->bin_bits,
                                                        ctx->n_bands > 1 ? (uint32_t)d.row0 : 0u,
-                                                       ctx->n_bands > 1 ? (uint32_t)d.row1 : 0xffffffffu);
-    d.bins_ready = with_bins;
+                                                       ctx->n_bands > 1 ? (uint32_t)d.row1 : 0xffffffffu,
+                                                       with_key && ctx->pack_samples ? d.samp_pack : nullptr);
     CUDA_TRY(cudaGetLastError());
     d.launches++;
+    d.bins_ready = with_bins;
     return XS_OK;
 }
 
@@ -686,6 +696,7 @@ int enqueue_grouped_back(xs_gpu_ctx *ctx, DeviceState &d)
     CUDA_TRY(cudaStreamSynchronize(d.stream));
     GroupedBatch b{};
     b.indirect = d.pending.indirect;
+    b.pack = b.indirect && ctx->pack_samples ? d.samp_pack + base : nullptr;
     b.energy = (b.indirect ? d.samp_e : d.grp_e) + base;
     b.where = (b.indirect ? d.samp_where : d.grp_where) + base;
     b.partial = d.sweep_partial + 3 * base;
@@ -1001,6 +1012,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
     ctx->e2e_kernel = env_int("XSB200_E2E_KERNEL", 6) == 4 ? 4 : 6;
     ctx->fuse_gather = env_int("XSB200_FUSE_GATHER", 1);
+    ctx->pack_samples = env_int("XSB200_PACK_SAMPLES", 1);
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
@@ -1165,7 +1177,8 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                 const int blocks = (int)std::min<long>((c_n + 255) / 256, (long)d.sm_count * 16);
                 xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
                                                                  d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
-                                                                 d.histogram + 16 * c);
+                                                                 d.histogram + 16 * c,
+                                                                 ctx->e2e_kernel == 6 && ctx->pack_samples ? d.samp_pack + c_lo : nullptr);
                 CUDA_TRY(cudaGetLastError());
                 d.launches++;
                 if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
@@ -1321,7 +1334,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         cudaFree(d.bin_count); cudaFree(d.bin_chunk_sum);
         xs::sort_scratch_free(d.sort);
-        cudaFree(d.samp_where); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
+        cudaFree(d.samp_where); cudaFree(d.samp_pack); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
         cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd); cudaFree(d.nuc_bucket);
         cudaFree(d.dump_macro);
         if (d.h_accum) cudaFreeHost(d.h_accum);

@@ -442,6 +442,7 @@ struct WindowArgs {
     int   n_seg;
     int   first_window, last_window;
     int   indirect;            // sorted kernel: energy / where are the UNGROUPED sample arrays, read through sample_id
+    const double2 *pack;       // indirect mode: (energy, row as the low word of .y) per sample -- one sector per random read
     WindowSegment seg[kMaxSegments];
 };
 
@@ -820,8 +821,14 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             // indirect: the sort's permutation is applied here instead of by a gather pass (two
             // random reads per lookup either way; -0.5 ms of gather kernel, +0.25 ms in here)
             const long src = A.indirect ? (long)A.sample_id[t] : t;
-            e[w] = A.energy[src];
-            where32[w] = A.where[src];
+            if (A.indirect && A.pack) {
+                const double2 s = __ldg(A.pack + src);
+                e[w] = s.x;
+                where32[w] = (uint32_t)__double_as_longlong(s.y);
+            } else {
+                e[w] = A.energy[src];
+                where32[w] = A.where[src];
+            }
         }
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
         const int ci = S.mat * kConcStride;
@@ -1069,7 +1076,7 @@ __global__ void xs_build_pairs_kernel(const double2 *grid, long n_iso, long n_gp
 __global__ void __launch_bounds__(256)
 xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, double *energy, int *mat,
                  uint32_t *where, uint32_t *key, unsigned int *mat_histogram, unsigned int *bin_count, int bin_shift,
-                 uint32_t row_begin, uint32_t row_end)
+                 uint32_t row_begin, uint32_t row_end, double2 *pack)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -1084,15 +1091,16 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
             const uint64_t s1 = lcg_step(s), s2 = lcg_step(s1);
             const int m = pick_material(lcg_to_double(s2));
             const double e = lcg_to_double(s1);
-            energy[t] = e;
-            mat[t] = m;
+            if (energy) energy[t] = e;
+            if (mat) mat[t] = m;
             bool mine = true;
-            if (where) {
+            if (where || pack) {
                 // energy-band sharding (unionized grid too large for one GPU): every device draws
                 // every lookup and keeps those whose row lies in its band [row_begin, row_end);
                 // the others get material 15 in the key (sorted to the end, never looked up)
                 const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
-                where[t] = w;
+                if (where) where[t] = w;
+                if (pack) pack[t] = make_double2(e, __longlong_as_double((long long)w));
                 mine = w >= row_begin && w < row_end;
             }
             const uint32_t k32 = ((mine ? (uint32_t)m : 15u) << 28) | (uint32_t)(s1 >> 35);
@@ -1147,7 +1155,7 @@ xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long
 // Same bookkeeping for samples that already exist (host-provided): where + histogram.
 __global__ void __launch_bounds__(256)
 xs_locate_kernel(const Problem P, int grid_type, long count, const double *energy, const int *mat,
-                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram)
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, double2 *pack)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -1156,7 +1164,9 @@ xs_locate_kernel(const Problem P, int grid_type, long count, const double *energ
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
         const double e = energy[t];
         const int m = mat[t];
-        where[t] = (uint32_t)locate_rt(P, grid_type, e);
+        const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
+        where[t] = w;
+        if (pack) pack[t] = make_double2(e, __longlong_as_double((long long)w));
         if (key) {    // same layout as the sampler's key: material, then 28 bits monotone in the energy
             const double scaled = fmin(fmax(e, 0.0) * 268435456.0, 268435455.0);
             key[t] = ((uint32_t)m << 28) | (uint32_t)scaled;
