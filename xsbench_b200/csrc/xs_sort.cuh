@@ -9,7 +9,7 @@
 // over bits 28..31, the fuel-first partition (-k 5) a single 1-bit pass.  The passes are
 // stable, so equal keys keep lookup-id order.
 //
-// Each pass = histogram (per 4096-key tile) -> exclusive scan of the digit-major
+// Each pass = histogram (per 2048-key tile) -> exclusive scan of the digit-major
 // [digit][tile] table -> stable scatter using warp match_any ranking; 32-bit keys are reordered
 // inside the tile (shared memory) before they are written, so the global writes are runs.
 #pragma once
@@ -18,9 +18,15 @@
 
 namespace xs {
 
+#ifndef XS_SCATTER_BLOCKS
+#define XS_SCATTER_BLOCKS 6
+#endif
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;                              // keys per thread
-constexpr int kSortTile = kSortThreads * kSortItems;        // 4096 keys per block
+#ifndef XS_SORT_ITEMS
+#define XS_SORT_ITEMS 8
+#endif
+constexpr int kSortItems = XS_SORT_ITEMS;                   // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;        // 2048 keys per block: small tiles, 6 blocks/SM (the scatter is latency-bound)
 constexpr int kRadix = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 
@@ -141,7 +147,7 @@ sort_scan_kernel(unsigned int *data, long total, const unsigned int *chunk_sum)
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(kSortThreads, sizeof(KeyT) == 4 ? XS_SCATTER_BLOCKS : 2)
 sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                     KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, long n, int shift,
                     uint32_t mask, int nonzero_flag, const unsigned int *__restrict__ tile_base, int n_tiles)
