@@ -213,7 +213,17 @@ XS_DEV long ueg_row_t(const Problem &P, double e)
         const double u = STREAM ? ldg_search_f64(P.ueg + mid) : __ldg(P.ueg + mid);
         if (u > e) hi = mid; else lo = mid + 1;
     }
-    while (lo < hi && !((STREAM ? ldg_search_f64(P.ueg + lo) : __ldg(P.ueg + lo)) > e)) lo++;
+    // the <= 4 remaining rows are probed at once (independent loads, no compare-then-load chain);
+    // the energies ascend, so "not greater than e" holds for a prefix of them
+    int not_greater = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (lo + k < hi) {
+            const double u = STREAM ? ldg_search_f64(P.ueg + lo + k) : __ldg(P.ueg + lo + k);
+            not_greater += !(u > e);
+        }
+    }
+    lo += not_greater;
     long row = lo - 1;
     if (row < 0) row = 0;
     if (row > P.n_ueg - 2) row = P.n_ueg - 2;
