@@ -40,9 +40,20 @@ class Problem:
         self.oracle.close()
 
 
-@pytest.fixture(scope="module", params=["unionized", "hash", "nuclide"])
+# Every grid type twice: with the default split of the sorted pipeline (at these sizes no material
+# has 64 lookups per grid interval, so xs_sorted_kernel does everything) and with XSB200_DENSE_MIN=1
+# (every material through xs_dense_kernel, sparse ones included: its per-lookup fallback runs a lot).
+# The knob is read once, by xs_gpu_init.
+@pytest.fixture(scope="module", params=[(g, dm) for g in ("unionized", "hash", "nuclide") for dm in (None, "1")],
+                ids=lambda p: p[0] + ("-dense" if p[1] else ""))
 def small(request):
-    p = Problem("small", 1000, request.param, 500, method="event", lookups=100000)
+    grid, dense_min = request.param
+    if dense_min:
+        os.environ["XSB200_DENSE_MIN"] = dense_min
+    try:
+        p = Problem("small", 1000, grid, 500, method="event", lookups=100000)
+    finally:
+        os.environ.pop("XSB200_DENSE_MIN", None)
     yield p
     p.close()
 
@@ -233,6 +244,10 @@ def test_gather_variants_agree(monkeypatch):
     {"XSB200_SORTED_KERNEL": "0"},      # windowed sweep on the sorted batch
     {"XSB200_KEY_LO_BIT": "26"},        # barely sorted: groups span many grid intervals -> direct-load path
     {"XSB200_E2E_KERNEL": "4"},         # host-sample API through partition + windowed sweep
+    {"XSB200_DENSE_MIN": "0"},          # no dense kernel at all
+    {"XSB200_DENSE_MIN": "20"},         # some materials dense, some not: two launches
+    {"XSB200_DENSE_MIN": "1", "XSB200_KEY_LO_BIT": "26"},   # dense kernel on a barely sorted batch: nearly every lookup resolves itself
+    {"XSB200_DENSE_MIN": "1", "XSB200_FUSE_GATHER": "0"},   # dense kernel on gathered (not indirect) samples
 ])
 @pytest.mark.parametrize("grid,hb", [("unionized", 500), ("hash", 500), ("nuclide", 500)])
 def test_sorted_pipeline_variants_agree(monkeypatch, env, grid, hb):
@@ -248,6 +263,29 @@ def test_sorted_pipeline_variants_agree(monkeypatch, env, grid, hb):
         res, macro = p.gpu.lookup_samples(e, m, want_macro_xs=True)
         v, omacro = p.oracle.lookup_samples(e, m)
         assert res.verification == v and np.array_equal(macro, omacro)
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("grid,hb", [("unionized", 50), ("hash", 50), ("nuclide", 50)])
+def test_dense_kernel_at_the_default_split(grid, hb):
+    """100 grid points per nuclide and 10^6 lookups: every material has >= 64 lookups per grid
+    interval, so the default split sends all of them to xs_dense_kernel (as large/fuel at 17 M).
+    Energies on grid points, one ulp around them and beyond every nuclide's ends are mixed in;
+    macro_xs must equal the oracle's bit for bit."""
+    p = Problem("small", 100, grid, hb, method="event", lookups=1_000_000)
+    try:
+        inp = xs.make_inputs(size="small", grid=grid, gridpoints=100, hash_bins=hb, method="event", lookups=1_000_000, kernel_id=6)
+        assert p.gpu.run(inp).verification == p.oracle.event(0, 1_000_000, NTHREADS)
+        rng = np.random.default_rng(17)
+        g = p.oracle.nuclide_grid[0::6]
+        e = np.concatenate([rng.random(400_000), g, np.nextafter(g, 0), np.nextafter(g, 1), [0.0, 5e-324, 1.0 - 2.0**-53]])
+        e = e[(e >= 0) & (e < 1)]
+        m = rng.integers(0, 12, len(e)).astype(np.int32)
+        res, macro = p.gpu.lookup_samples(e, m, want_macro_xs=True)
+        v, omacro = p.oracle.lookup_samples(e, m)
+        assert res.verification == v and res.n_lookups == len(e)
+        assert np.array_equal(macro, omacro)
     finally:
         p.close()
 

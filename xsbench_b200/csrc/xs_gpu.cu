@@ -145,6 +145,7 @@ struct xs_gpu_ctx {
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
+    int dense_min = 64;                    // -k 6: materials with >= this many lookups per grid interval go to xs_dense_kernel (0 = never)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
     size_t smem_bytes = 0;
@@ -512,43 +513,53 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
     return XS_OK;
 }
 
-// Lane-per-lookup sweep over a batch sorted by (material, energy): every material in one launch.
+// Lane-per-lookup sweep over a batch sorted by (material, energy): the materials with many lookups
+// per grid interval (>= ctx->dense_min: a warp-group's 64 lookups then fall into the first lookup's
+// interval or the next) go to xs_dense_kernel, the others to xs_sorted_kernel -- two launches.
 int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::BatchSink sink)
 {
-    static const WindowKernel table[3] = { xs::xs_sorted_kernel<xs::kUnionized>, xs::xs_sorted_kernel<xs::kNuclide>,
-                                           xs::xs_sorted_kernel<xs::kHash> };
-    xs::WindowArgs a{};
-    long groups = 0;
-    for (int m = 0; m < XS_NUM_MATERIALS; m++) {
-        if (b.count[m] <= 0) continue;
-        xs::WindowSegment &sgm = a.seg[a.n_seg++];
-        sgm.mat = m; sgm.first = d.h_mat_first[m]; sgm.j_begin = 0; sgm.j_end = ctx->num_nucs[m];
-        sgm.offset = b.offset[m];
-        sgm.count = (int)b.count[m];
-        sgm.group_begin = (int)groups;
-        groups += (b.count[m] + xs::kSortedGroup - 1) / xs::kSortedGroup;
+    static const WindowKernel table[2][3] = {
+        { xs::xs_sorted_kernel<xs::kUnionized>, xs::xs_sorted_kernel<xs::kNuclide>, xs::xs_sorted_kernel<xs::kHash> },
+        { xs::xs_dense_kernel<xs::kUnionized>, xs::xs_dense_kernel<xs::kNuclide>, xs::xs_dense_kernel<xs::kHash> } };
+    for (int dense = 1; dense >= 0; dense--) {
+        xs::WindowArgs a{};
+        long groups = 0;
+        for (int m = 0; m < XS_NUM_MATERIALS; m++) {
+            if (b.count[m] <= 0) continue;
+            const bool is_dense = ctx->dense_min > 0 && b.count[m] >= (long)ctx->dense_min * d.P.n_gp;
+            if (is_dense != (dense == 1)) continue;
+            xs::WindowSegment &sgm = a.seg[a.n_seg++];
+            sgm.mat = m; sgm.first = d.h_mat_first[m]; sgm.j_begin = 0; sgm.j_end = ctx->num_nucs[m];
+            sgm.offset = b.offset[m];
+            sgm.count = (int)b.count[m];
+            sgm.group_begin = (int)groups;
+            groups += (b.count[m] + xs::kSortedGroup - 1) / xs::kSortedGroup;
+        }
+        if (groups == 0) continue;
+        a.n_groups = (int)groups;
+        a.energy = b.energy;
+        a.where = b.where;
+        a.sample_id = b.id;
+        a.indirect = b.indirect;
+        a.pack = b.pack;
+        a.first_window = a.last_window = 1;
+        WindowKernel k = table[dense][ctx->grid_type];
+        int blocks = 0;
+        size_t staged = 0;
+        if (dense)
+            staged = (size_t)xs::kWarpsPerBlock * (xs::kDenseRingBytes + xs::kDenseFirstWords * sizeof(uint32_t));
+        else if (ctx->grid_type == XS_UNIONIZED)
+            staged = (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes);
+        const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
+        CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
+        if (rc != XS_OK) return rc;
+        const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+        if (blocks > max_useful) blocks = (int)max_useful;
+        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
     }
-    if (groups == 0) return XS_OK;
-    a.n_groups = (int)groups;
-    a.energy = b.energy;
-    a.where = b.where;
-    a.sample_id = b.id;
-    a.indirect = b.indirect;
-    a.pack = b.pack;
-    a.first_window = a.last_window = 1;
-    WindowKernel k = table[ctx->grid_type];
-    int blocks = 0;
-    const size_t staged = ctx->grid_type == XS_UNIONIZED
-                              ? (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes) : 0;
-    const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
-    CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
-    if (rc != XS_OK) return rc;
-    const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
-    if (blocks > max_useful) blocks = (int)max_useful;
-    k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink);
-    CUDA_TRY(cudaGetLastError());
-    d.launches++;
     return XS_OK;
 }
 
@@ -1014,6 +1025,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->fuse_gather = env_int("XSB200_FUSE_GATHER", 1);
     ctx->pack_samples = env_int("XSB200_PACK_SAMPLES", 1);
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
+    ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);

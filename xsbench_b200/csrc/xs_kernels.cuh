@@ -773,6 +773,9 @@ XS_DEV PairRecord ldg_record(const double2 *rec)
     return r;
 }
 
+#ifndef XS_EXP
+#define XS_EXP 0
+#endif
 XS_DEV void record_step(const PairRecord &r, double e, double conc, double acc[5])
 {
     const double n = r.hi_e - e;
@@ -987,6 +990,277 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     lane_step(rb, no_b, j + 1);
                 }
             }
+        }
+
+#pragma unroll
+        for (int w = 0; w < kPerLane; w++) {
+            if (!on[w]) continue;
+            double gap;
+            const int am = argmax5(acc[w], gap);
+            my_sum += (unsigned int)(am + 1);
+            if (sink.macro_out) {
+                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
+#pragma unroll
+                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[w][k];
+            }
+            if (sink.fwd_out) {            // history mode feedback (openmp-threading/Simulation.c:225-228)
+                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
+                int fwd = 0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) fwd += acc[w][k] > 1.0;
+                sink.fwd_out[id] = (unsigned char)fwd;
+            }
+        }
+    }
+    const unsigned long long bs = block_sum(my_sum, s_part);
+    if (threadIdx.x == 0) {
+        if (bs) atomicAdd(sink.accum, bs);
+        if (blockIdx.x == 0) {                               // lookups completed by this launch
+            unsigned long long done = 0;
+            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
+            atomicAdd(sink.accum + 1, done);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// xs_dense_kernel -- the sorted kernel for DENSE segments (many lookups per grid interval:
+// large/fuel has 209).  The 64 energy-sorted lookups of a warp-group then fall, per nuclide,
+// into ONE grid interval (73 % of the steps of large/fuel) or a few consecutive ones.  So only
+// the group's lowest and highest energy are resolved (lane l resolves nuclide c0 + l: two
+// index-row segments per group and chunk instead of 64, or two bucket-table searches per nuclide
+// instead of 64 in hash / nuclide mode), which gives, per nuclide, the first record k_min and
+// the number of records n = k_max - k_min + 1 the group can touch (the search is monotone in
+// the energy).  n records (at most kDenseSpan) go through the shared-memory ring.
+//   n == 1: every lookup of the group uses that record -- no per-lookup work at all;
+//   n >= 2: a lookup picks its record by comparing its energy with the interval bounds stored in
+//           the ring records; a lookup beyond the ring, or exactly ON a bound (where the
+//           reference's hash-grid procedure has its own ideas), resolves its own interval with
+//           the reference's procedure (nuclide_low).
+// Results therefore never depend on how well the batch is sorted: min / max are taken over the
+// group, not assumed from positions.  The next chunk is resolved (and its records requested
+// into L2) before the current one is gathered: no staging phase, no transposition, 1/32 of the
+// index-grid traffic of xs_sorted_kernel.
+// ---------------------------------------------------------------------------------------
+#ifndef XS_DENSE_BLOCKS
+#define XS_DENSE_BLOCKS 2
+#endif
+#ifndef XS_DENSE_RING
+#define XS_DENSE_RING 8
+#endif
+#ifndef XS_DENSE_SPAN
+#define XS_DENSE_SPAN 4
+#endif
+constexpr int kDenseRing = XS_DENSE_RING;              // steps of records in flight per warp (a power of two)
+constexpr int kDenseSpan = XS_DENSE_SPAN;              // records per ring slot (2..4)
+constexpr int kDenseSlotBytes = kDenseSpan * 128;
+constexpr int kDenseRingBytes = kDenseRing * kDenseSlotBytes;
+constexpr int kDenseFirstWords = 2 * 32 * 2;           // per warp: (first record, record count) per step, double-buffered by chunk
+static_assert((kDenseRing & (kDenseRing - 1)) == 0 && kDenseSpan >= 2 && kDenseSpan <= 4, "dense kernel ring geometry");
+
+XS_DEV uint2 lds_v2_u32(uint32_t smem_addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr));
+    return v;
+}
+XS_DEV long long lds_s64(uint32_t smem_addr)
+{
+    long long v;
+    asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(smem_addr));
+    return v;
+}
+
+template <int GRID>
+__global__ void __launch_bounds__(kBlockThreads, XS_DENSE_BLOCKS)
+xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
+{
+    __shared__ unsigned long long s_part[kWarpsPerBlock];
+    extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][(first record, count) per step][nuclide ids]
+    uint32_t *s_first = s_dyn + kWarpsPerBlock * kDenseRingBytes / 4;
+    int *s_nuc = (int *)(s_first + kWarpsPerBlock * kDenseFirstWords);
+    for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int my_sum = 0;
+    uint2 *warp_first = (uint2 *)(s_first + warp * kDenseFirstWords);
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + warp * kDenseRingBytes;
+    const uint32_t first_base = (uint32_t)__cvta_generic_to_shared(warp_first);
+
+    for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
+        int sg = 0;
+        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;      // warp-uniform, <= 11 steps
+        const WindowSegment &S = A.seg[sg];
+        const int group_first = (g - S.group_begin) * kSortedGroup;
+        const int first_in_seg = group_first + lane * kPerLane;
+        const long t0 = S.offset + first_in_seg;
+        double e[kPerLane];
+        uint32_t where32[kPerLane];
+        bool on[kPerLane];
+#pragma unroll
+        for (int w = 0; w < kPerLane; w++) {
+            on[w] = first_in_seg + w < S.count;
+            // idle slots repeat the group's first lookup (results dropped)
+            const long t = on[w] ? t0 + w : S.offset + group_first;
+            const long src = A.indirect ? (long)A.sample_id[t] : t;
+            if (A.indirect && A.pack) {
+                const double2 s = __ldg(A.pack + src);
+                e[w] = s.x;
+                where32[w] = (uint32_t)__double_as_longlong(s.y);
+            } else {
+                e[w] = A.energy[src];
+                where32[w] = A.where[src];
+            }
+        }
+        // The group's energy range.  Energies are non-negative doubles: their bit patterns order
+        // like the values (and 64-bit integer compares run on the ALU pipe instead of queueing
+        // behind the FP64 work).  The UEG row / hash bin is monotone in the energy, so the
+        // extreme rows belong to the extreme energies.
+        long long eb_min = __double_as_longlong(e[0]), eb_max = eb_min;
+        uint32_t where_min = where32[0], where_max = where32[0];
+#pragma unroll
+        for (int w = 1; w < kPerLane; w++) {
+            eb_min = min(eb_min, __double_as_longlong(e[w]));
+            eb_max = max(eb_max, __double_as_longlong(e[w]));
+            where_min = min(where_min, where32[w]);
+            where_max = max(where_max, where32[w]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            eb_min = min(eb_min, __shfl_xor_sync(kFullMask, eb_min, off));
+            eb_max = max(eb_max, __shfl_xor_sync(kFullMask, eb_max, off));
+        }
+        where_min = __reduce_min_sync(kFullMask, where_min);
+        where_max = __reduce_max_sync(kFullMask, where_max);
+        const double e_min = __longlong_as_double(eb_min), e_max = __longlong_as_double(eb_max);
+
+        const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
+        const int ci = S.mat * kConcStride;
+        double acc[kPerLane][5];
+#pragma unroll
+        for (int w = 0; w < kPerLane; w++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
+
+        // lane l: the records the group can touch in nuclide c + l (columns past the end repeat
+        // the material's last nuclide: valid records, only ever used with concentration 0)
+        uint32_t multi_next = 0;
+        auto resolve = [&](int c, int buf) {
+            const int nuc_l = s_nuc[S.first + min(c + lane, n_nuc - 1)];
+            const int k_lo = nuclide_low<GRID, false>(P, e_min, (long)where_min, nuc_l);
+            const int k_hi = nuclide_low<GRID, false>(P, e_max, (long)where_max, nuc_l);
+            int n = k_hi - k_lo + 1;
+            // The hash-grid procedure maps an energy that EQUALS the grid point at the edge of its
+            // bin's bracket to the nuclide's first / last interval (cuda/Simulation.cu:150-156).
+            // Should both ends of the group be such points, the lookups in between are not: let
+            // every lookup of this step resolve itself (n = 0).
+            if (GRID == kHash && k_lo == k_hi && (k_lo == 0 || k_lo == P.n_gp - 2)) n = 0;
+            if (n < 0) n = 0;
+            const uint32_t no = (uint32_t)nuc_l * (uint32_t)P.n_gp + (uint32_t)k_lo;
+            warp_first[buf * 32 + lane] = make_uint2(no, (uint32_t)n);
+            multi_next = __ballot_sync(kFullMask, n != 1);  // bit l: step l of that chunk needs the per-lookup selection
+            // a record is used by ~one block only, so its first touch comes from DRAM: start now
+            prefetch_l2(P.pairs + 8 * (size_t)no);
+#pragma unroll
+            for (int i = 1; i < kDenseSpan; i++)
+                if (i < n) prefetch_l2(P.pairs + 8 * ((size_t)no + i));
+        };
+        __syncwarp();
+        resolve(0, 0);
+        int buf = 0;
+        for (int c0 = 0; c0 < n_nuc; c0 += 32, buf ^= 1) {
+            const uint32_t multi = multi_next;               // known a chunk ahead, in a register: no load in front of the branch
+            const int jn = min(32, n_nuc - c0);
+            const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
+            const int *nucs = s_nuc + S.first + c0;
+            __syncwarp();
+            if (GRID == kUnionized && c0 + 64 < n_nuc) {      // the index-row segments of the chunk after the next
+                const uint32_t row_w = (lane & 1) ? where_max : where_min;
+                const int *row = P.index_grid + (size_t)row_w * (uint32_t)P.n_iso;
+                if (lane < 2)        prefetch_l2(row + nucs[64]);
+                else if (lane >= 30) prefetch_l2(row + nucs[min(95, n_nuc - c0 - 1)]);
+            }
+            if (c0 + 32 < n_nuc) resolve(c0 + 32, buf ^ 1);
+
+            const uint32_t first_addr = first_base + (uint32_t)(buf * 32 * 8);   // shared address of this chunk's (first, count) pairs
+            auto issue = [&](int s) {                        // steps s, s+1: 8 lanes x 16 B per record
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int step = s + q;
+                    if (step < n_steps) {
+                        const uint2 fc = lds_v2_u32(first_addr + step * 8);
+                        const uint32_t pieces = 8u * min(max(fc.y, 1u), (uint32_t)kDenseSpan);
+                        if ((uint32_t)lane < pieces)
+                            cp_async_16(ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes + lane * 16),
+                                        P.pairs + 8 * (size_t)fc.x + lane);
+                    }
+                }
+                cp_async_commit();
+            };
+            auto resolve_own = [&](PairRecord &r, double e_w, uint32_t where_w, int step) {
+                const int nuc = nucs[min(step, jn - 1)];
+                const uint32_t no = (uint32_t)nuc * (uint32_t)P.n_gp
+                                    + (uint32_t)nuclide_low<GRID, false>(P, e_w, (long)where_w, nuc);
+                r = ldg_record(P.pairs + 8 * (size_t)no);
+            };
+#pragma unroll
+            for (int s = 0; s < kDenseRing; s += 2) issue(s);
+            const int conc_base = ci + c0;
+            for (int j = 0; j < n_steps; j += 2) {
+                cp_async_wait_group<kDenseRing / 2 - 1>();
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int step = j + h;
+                    const double conc = c_conc_pad[conc_base + step];
+                    const uint32_t slot = ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes);
+                    PairRecord r;
+#if XS_EXP == 2      // timing experiment: no selection
+                    if (true) {
+#else
+                    if (!((multi >> step) & 1u)) {           // one record for the whole group (warp-uniform)
+#endif
+                        r = lds_record(slot);
+#pragma unroll
+                        for (int w = 0; w < kPerLane; w++) record_step(r, e[w], conc, acc[w]);
+                    } else {
+                        // interval bounds: record i covers (hi[i-1], hi[i]); a bound past the group's n
+                        // records is stale, but it is only looked at by a lookup already beyond them.
+                        // (The last record's own bound matters when the group spans more than the ring.)
+                        long long hi[kDenseSpan];
+#pragma unroll
+                        for (int i = 0; i < kDenseSpan; i++) hi[i] = lds_s64(slot + i * 128 + 96);
+                        const uint32_t n_ring = min(lds_v2_u32(first_addr + step * 8).y, (uint32_t)kDenseSpan);
+                        uint32_t prev_addr = 0;
+                        bool prev_ok = false;
+#pragma unroll
+                        for (int w = 0; w < kPerLane; w++) {
+                            const long long eb = __double_as_longlong(e[w]);
+                            uint32_t which = 0;
+                            bool beyond = true, on_bound = false;
+#pragma unroll
+                            for (int i = 0; i < kDenseSpan; i++) {
+                                beyond = beyond & (eb > hi[i]);
+                                which += beyond ? 1u : 0u;
+                                on_bound = on_bound | (eb == hi[i]);
+                            }
+                            const bool ok = (which < n_ring) & !on_bound;
+                            const uint32_t addr = slot + min(which, (uint32_t)(kDenseSpan - 1)) * 128;
+                            if (w == 0 || addr != prev_addr || !ok || !prev_ok) {
+                                r = lds_record(addr);
+                                if (!ok) resolve_own(r, e[w], where32[w], step);
+                            }
+                            prev_addr = addr;
+                            prev_ok = ok;
+                            record_step(r, e[w], conc, acc[w]);
+                        }
+                    }
+                }
+                __syncwarp();                                // everyone is done with these two slots
+                issue(j + kDenseRing);
+            }
+            cp_async_wait_group<0>();
         }
 
 #pragma unroll
