@@ -749,13 +749,14 @@ template <int N> XS_DEV void cp_async_wait_group() { asm volatile("cp.async.wait
 XS_DEV PairRecord lds_record(uint32_t smem_addr)
 {
     PairRecord r;
+    // (hi.E, d, 1/d) first: the interpolation factor is the head of the dependency chain
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+96];" : "=d"(r.hi_e), "=d"(r.d) : "r"(smem_addr));
+    asm volatile("ld.shared.f64 %0, [%1+112];" : "=d"(r.inv) : "r"(smem_addr));
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.hi[0]), "=d"(r.dlt[0]) : "r"(smem_addr));
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(r.hi[1]), "=d"(r.dlt[1]) : "r"(smem_addr));
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+32];" : "=d"(r.hi[2]), "=d"(r.dlt[2]) : "r"(smem_addr));
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+48];" : "=d"(r.hi[3]), "=d"(r.dlt[3]) : "r"(smem_addr));
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+64];" : "=d"(r.hi[4]), "=d"(r.dlt[4]) : "r"(smem_addr));
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+96];" : "=d"(r.hi_e), "=d"(r.d) : "r"(smem_addr));
-    asm volatile("ld.shared.f64 %0, [%1+112];" : "=d"(r.inv) : "r"(smem_addr));
     r.pad = 0.0;
     return r;
 }
@@ -1145,7 +1146,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 
         // lane l: the records the group can touch in nuclide c + l (columns past the end repeat
         // the material's last nuclide: valid records, only ever used with concentration 0)
-        uint32_t multi_next = 0;
+        uint32_t multi_next = 0, two_next = 0;
         auto resolve = [&](int c, int buf) {
             const int nuc_l = s_nuc[S.first + min(c + lane, n_nuc - 1)];
             const int k_lo = nuclide_low<GRID, false>(P, e_min, (long)where_min, nuc_l);
@@ -1156,21 +1157,47 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             // Should both ends of the group be such points, the lookups in between are not: let
             // every lookup of this step resolve itself (n = 0).
             if (GRID == kHash && k_lo == k_hi && (k_lo == 0 || k_lo == P.n_gp - 2)) n = 0;
-            if (n < 0) n = 0;
+            n = min(max(n, 0), 0xffff);
             const uint32_t no = (uint32_t)nuc_l * (uint32_t)P.n_gp + (uint32_t)k_lo;
-            warp_first[buf * 32 + lane] = make_uint2(no, (uint32_t)n);
+            // (count in the low half, the number of 16-byte pieces the ring copy moves in the high half)
+            const uint32_t pieces = 8u * (uint32_t)min(max(n, 1), kDenseSpan);
+            warp_first[buf * 32 + lane] = make_uint2(no, (uint32_t)n | (pieces << 16));
             multi_next = __ballot_sync(kFullMask, n != 1);  // bit l: step l of that chunk needs the per-lookup selection
+            two_next = __ballot_sync(kFullMask, n == 2);
             // a record is used by ~one block only, so its first touch comes from DRAM: start now
             prefetch_l2(P.pairs + 8 * (size_t)no);
 #pragma unroll
             for (int i = 1; i < kDenseSpan; i++)
                 if (i < n) prefetch_l2(P.pairs + 8 * ((size_t)no + i));
         };
+        // The warp's next group: fetch its sample ids now, request the samples behind them after
+        // the first chunk (two dependent random reads otherwise wait in front of every group).
+        uint32_t next_id[kPerLane];
+        bool next_any = false;
+        if (A.indirect && A.pack) {
+            const int g2 = g + gridDim.x * kWarpsPerBlock;
+            if (g2 < A.n_groups) {
+                int s2 = sg;
+                while (s2 + 1 < A.n_seg && g2 >= A.seg[s2 + 1].group_begin) s2++;
+                const WindowSegment &S2 = A.seg[s2];
+                const int first2 = (g2 - S2.group_begin) * kSortedGroup + lane * kPerLane;
+                next_any = true;
+#pragma unroll
+                for (int w = 0; w < kPerLane; w++)
+                    next_id[w] = A.sample_id[S2.offset + min(first2 + w, S2.count - 1)];
+            }
+        }
         __syncwarp();
         resolve(0, 0);
         int buf = 0;
         for (int c0 = 0; c0 < n_nuc; c0 += 32, buf ^= 1) {
-            const uint32_t multi = multi_next;               // known a chunk ahead, in a register: no load in front of the branch
+            if (c0 == 32 || (c0 == 0 && n_nuc <= 32)) {
+                if (next_any) {
+#pragma unroll
+                    for (int w = 0; w < kPerLane; w++) prefetch_l2(A.pack + next_id[w]);
+                }
+            }
+            const uint32_t multi = multi_next, two = two_next;   // known a chunk ahead, in registers: no load in front of the branches
             const int jn = min(32, n_nuc - c0);
             const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
             const int *nucs = s_nuc + S.first + c0;
@@ -1184,17 +1211,15 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             if (c0 + 32 < n_nuc) resolve(c0 + 32, buf ^ 1);
 
             const uint32_t first_addr = first_base + (uint32_t)(buf * 32 * 8);   // shared address of this chunk's (first, count) pairs
-            auto issue = [&](int s) {                        // steps s, s+1: 8 lanes x 16 B per record
+            // steps s, s+1 with their (first record, count) pairs: 8 lanes x 16 B per record
+            auto issue = [&](int s, uint2 d0, uint2 d1) {
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
                     const int step = s + q;
-                    if (step < n_steps) {
-                        const uint2 fc = lds_v2_u32(first_addr + step * 8);
-                        const uint32_t pieces = 8u * min(max(fc.y, 1u), (uint32_t)kDenseSpan);
-                        if ((uint32_t)lane < pieces)
-                            cp_async_16(ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes + lane * 16),
-                                        P.pairs + 8 * (size_t)fc.x + lane);
-                    }
+                    const uint2 fc = q ? d1 : d0;
+                    if (step < n_steps && (uint32_t)lane < (fc.y >> 16))
+                        cp_async_16(ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes + lane * 16),
+                                    P.pairs + 8 * (size_t)fc.x + lane);
                 }
                 cp_async_commit();
             };
@@ -1205,7 +1230,11 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 r = ldg_record(P.pairs + 8 * (size_t)no);
             };
 #pragma unroll
-            for (int s = 0; s < kDenseRing; s += 2) issue(s);
+            for (int s = 0; s < kDenseRing; s += 2)
+                issue(s, lds_v2_u32(first_addr + s * 8), lds_v2_u32(first_addr + (s + 1) * 8));
+            // the pairs of the steps issued at the end of an iteration are fetched one iteration
+            // ahead (no load in front of the copy instructions)
+            uint2 d0 = lds_v2_u32(first_addr + (kDenseRing & 31) * 8), d1 = lds_v2_u32(first_addr + ((kDenseRing + 1) & 31) * 8);
             const int conc_base = ci + c0;
             for (int j = 0; j < n_steps; j += 2) {
                 cp_async_wait_group<kDenseRing / 2 - 1>();
@@ -1215,50 +1244,64 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     const int step = j + h;
                     const double conc = c_conc_pad[conc_base + step];
                     const uint32_t slot = ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes);
-                    PairRecord r;
-#if XS_EXP == 2      // timing experiment: no selection
-                    if (true) {
-#else
-                    if (!((multi >> step) & 1u)) {           // one record for the whole group (warp-uniform)
-#endif
-                        r = lds_record(slot);
+                    // which ring record each of the lane's lookups uses, and whether that is settled
+                    uint32_t addr[kPerLane];
+                    bool ok[kPerLane];
 #pragma unroll
-                        for (int w = 0; w < kPerLane; w++) record_step(r, e[w], conc, acc[w]);
-                    } else {
-                        // interval bounds: record i covers (hi[i-1], hi[i]); a bound past the group's n
-                        // records is stale, but it is only looked at by a lookup already beyond them.
-                        // (The last record's own bound matters when the group spans more than the ring.)
-                        long long hi[kDenseSpan];
+                    for (int w = 0; w < kPerLane; w++) { addr[w] = slot; ok[w] = true; }
+#if XS_EXP != 2      // (timing experiment 2: no selection)
+                    if ((multi >> step) & 1u) {              // warp-uniform: more (or fewer) than one record
+                        if ((two >> step) & 1u) {
+                            // two records: one bound between them.  Nothing lies beyond the second
+                            // (the search is monotone); ON the bound the reference decides.
+                            const long long hi0 = lds_s64(slot + 96);
 #pragma unroll
-                        for (int i = 0; i < kDenseSpan; i++) hi[i] = lds_s64(slot + i * 128 + 96);
-                        const uint32_t n_ring = min(lds_v2_u32(first_addr + step * 8).y, (uint32_t)kDenseSpan);
-                        uint32_t prev_addr = 0;
-                        bool prev_ok = false;
-#pragma unroll
-                        for (int w = 0; w < kPerLane; w++) {
-                            const long long eb = __double_as_longlong(e[w]);
-                            uint32_t which = 0;
-                            bool beyond = true, on_bound = false;
-#pragma unroll
-                            for (int i = 0; i < kDenseSpan; i++) {
-                                beyond = beyond & (eb > hi[i]);
-                                which += beyond ? 1u : 0u;
-                                on_bound = on_bound | (eb == hi[i]);
+                            for (int w = 0; w < kPerLane; w++) {
+                                const long long eb = __double_as_longlong(e[w]);
+                                addr[w] = slot + (eb > hi0 ? 128u : 0u);
+                                ok[w] = eb != hi0;
                             }
-                            const bool ok = (which < n_ring) & !on_bound;
-                            const uint32_t addr = slot + min(which, (uint32_t)(kDenseSpan - 1)) * 128;
-                            if (w == 0 || addr != prev_addr || !ok || !prev_ok) {
-                                r = lds_record(addr);
-                                if (!ok) resolve_own(r, e[w], where32[w], step);
+                        } else {
+                            // record i covers (hi[i-1], hi[i]); a bound past the group's n records is
+                            // stale, but it is only looked at by a lookup already beyond them.  (The
+                            // last record's own bound matters when the group spans more than the ring.)
+                            long long hi[kDenseSpan];
+#pragma unroll
+                            for (int i = 0; i < kDenseSpan; i++) hi[i] = lds_s64(slot + i * 128 + 96);
+                            const uint32_t n_ring = min(lds_v2_u32(first_addr + step * 8).y & 0xffffu, (uint32_t)kDenseSpan);
+#pragma unroll
+                            for (int w = 0; w < kPerLane; w++) {
+                                const long long eb = __double_as_longlong(e[w]);
+                                uint32_t which = 0;
+                                bool beyond = true, on_bound = false;
+#pragma unroll
+                                for (int i = 0; i < kDenseSpan; i++) {
+                                    beyond = beyond & (eb > hi[i]);
+                                    which += beyond ? 1u : 0u;
+                                    on_bound = on_bound | (eb == hi[i]);
+                                }
+                                ok[w] = (which < n_ring) & !on_bound;
+                                addr[w] = slot + min(which, (uint32_t)(kDenseSpan - 1)) * 128;
                             }
-                            prev_addr = addr;
-                            prev_ok = ok;
-                            record_step(r, e[w], conc, acc[w]);
                         }
+                    }
+#endif
+                    PairRecord r = lds_record(addr[0]);
+                    if (!ok[0]) resolve_own(r, e[0], where32[0], step);
+                    record_step(r, e[0], conc, acc[0]);
+#pragma unroll
+                    for (int w = 1; w < kPerLane; w++) {
+                        if (addr[w] != addr[w - 1] || !ok[w] || !ok[w - 1]) {
+                            r = lds_record(addr[w]);
+                            if (!ok[w]) resolve_own(r, e[w], where32[w], step);
+                        }
+                        record_step(r, e[w], conc, acc[w]);
                     }
                 }
                 __syncwarp();                                // everyone is done with these two slots
-                issue(j + kDenseRing);
+                issue(j + kDenseRing, d0, d1);
+                d0 = lds_v2_u32(first_addr + ((j + 2 + kDenseRing) & 31) * 8);
+                d1 = lds_v2_u32(first_addr + ((j + 3 + kDenseRing) & 31) * 8);
             }
             cp_async_wait_group<0>();
         }
