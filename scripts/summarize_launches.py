@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an ncu launch list (csv from `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
 dram__bytes_write.sum --csv`) of bench.py: per-kernel share of ONE timed step of the headline
-pipeline (-k 6: sample -> radix sort -> lane-per-lookup kernel).
+pipeline (-k 6: sample -> radix sort -> lane-per-lookup kernels xs_dense_kernel + xs_sorted_kernel).
 usage: summarize_launches.py profiles/rNN_launches.csv rNN [bound-summary text]"""
 import collections, csv, json, os, sys
 path, tag = sys.argv[1], sys.argv[2]
@@ -15,7 +15,7 @@ for r in rows[1:]:
     d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(',', ''))
 launches = list(d.items())
 names = [k[1] for k, _ in launches]
-STEP = ('xs_sample_kernel', 'sort_', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel')
+STEP = ('xs_sample_kernel', 'sort_', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel', 'xs_dense_kernel')
 starts = [i for i, n in enumerate(names) if 'xs_sample_kernel' in n]
 i0 = starts[2]                                   # steps: warm-up, timed 1, timed 2 -> take timed 2
 i1 = i0 + 1
@@ -47,6 +47,9 @@ json.dump({"kernel": f"{dom_name}: {w[0]} launch(es) per step",
            "dram_bytes_per_launch": (w[2] + w[3]) / w[0], "launches_per_step": w[0], "share_of_step": w[1] / tot,
            "what_bounds_it": bound or "see profiles/%s_notes.md" % tag,
            "source": f"profiles/{os.path.basename(path)} (ncu, one timed step of bench.py)",
+           "lookup_phase": "xs_dense_kernel + xs_sorted_kernel (2 launches per step)",
+           "lookup_phase_dram_bytes": sum(a[2] + a[3] for k, a in agg.items() if 'xs_dense_kernel' in k or 'xs_sorted_kernel' in k or 'xs_window_kernel' in k),
+           "lookup_phase_share_of_step": sum(a[1] for k, a in agg.items() if 'xs_dense_kernel' in k or 'xs_sorted_kernel' in k or 'xs_window_kernel' in k) / tot,
            "dram_bytes_per_step_all_kernels": sum(a[2] + a[3] for a in agg.values())},
           open(os.path.join(out_dir, "lookup_kernel_traffic.json"), 'w'), indent=1)
 print("\n".join(L[:20]))

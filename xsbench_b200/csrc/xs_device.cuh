@@ -262,7 +262,10 @@ XS_DEV int search_nuclide_rec(const Problem &P, long base, double e, int lo, int
 }
 
 // REC = false: energies from the reference-layout grid; REC = true: from the pair records.
-template <int GRID, bool REC = false>
+// WIDE = true: the last <= 4 candidates of a search are probed at once (independent loads: fewer
+//               round trips -- the latency-bound callers); false: one probe at a time (fewer
+//               loads -- the windowed sweep, which is bound by its L1 traffic).
+template <int GRID, bool REC = false, bool WIDE = true>
 XS_DEV int nuclide_low(const Problem &P, double e, long where, int nuc)
 {
     const int last = P.n_gp - 1;
@@ -282,7 +285,17 @@ XS_DEV int nuclide_low(const Problem &P, double e, long where, int nuc)
                 const int mid = lo + (hi - lo) / 2;
                 if (ldg_grid_energy(g + 3 * (long)mid) > e) hi = mid; else lo = mid + 1;
             }
-            while (lo < hi && !(ldg_grid_energy(g + 3 * (long)lo) > e)) lo++;
+            // the <= 4 remaining points are probed at once (independent loads); the energies
+            // ascend, so "not greater than e" holds for a prefix of them
+            if (WIDE) {
+                int not_greater = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (lo + k < hi) not_greater += !(ldg_grid_energy(g + 3 * (long)(lo + k)) > e);
+                lo += not_greater;
+            } else {
+                while (lo < hi && !(ldg_grid_energy(g + 3 * (long)lo) > e)) lo++;
+            }
             low = lo - 1;
             if (low < 0) low = 0;
         } else {
@@ -297,6 +310,20 @@ XS_DEV int nuclide_low(const Problem &P, double e, long where, int nuc)
         const double e_hi = REC ? rec_energy(P, base, u_hi) : ldg_grid_energy(g + 3 * (long)u_hi);
         if (e <= e_lo)      low = 0;
         else if (e >= e_hi) low = last;
+        else if (WIDE && u_hi - u_lo <= 5) {
+            // e_lo < e < e_hi: the bisection returns u_lo + #{interior points <= e} (the energies
+            // ascend).  A hash bin brackets ~3 points: probe the interior ones at once
+            // (independent loads) instead of bisecting (dependent ones).
+            int not_greater = 0;
+#pragma unroll
+            for (int k = 1; k <= 4; k++) {
+                if (u_lo + k < u_hi) {
+                    const double ek = REC ? rec_energy(P, base, u_lo + k) : ldg_grid_energy(g + 3 * (long)(u_lo + k));
+                    not_greater += !(ek > e);
+                }
+            }
+            low = u_lo + not_greater;
+        }
         else                low = REC ? search_nuclide_rec(P, base, e, u_lo, u_hi) : search_nuclide(g, e, u_lo, u_hi);
     }
     return low == last ? last - 1 : low;

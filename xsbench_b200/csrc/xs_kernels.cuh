@@ -520,7 +520,7 @@ XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1]
         double e_s = 0.0;
         if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
         low[r] = 0;
-        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID, GRID == kHash>(P, e_s, (long)w_s, nuc);   // hash: probe the records (measured faster); nuclide: the compact grid
+        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID, GRID == kHash, false>(P, e_s, (long)w_s, nuc);   // hash: probe the records (measured faster); nuclide: the compact grid
     }
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
