@@ -38,7 +38,7 @@ L.append(f"| **total** | {sum(a[0] for a in agg.values())} | {tot/1e3:.1f} | 100
 dom_name, w = max(agg.items(), key=lambda kv: kv[1][1])
 L += ["", f"Dominant kernel `{dom_name}`: {w[0]} launch(es) per step, {100*w[1]/tot:.1f} % of the step; DRAM traffic "
       f"{(w[2]+w[3])/1e9:.2f} GB per launch against 97.1 GB of algorithmic gather bytes (SURVEY 8d): the pair records are shared by "
-      "the lookups of a warp and served from L1/L2; DRAM streams the index rows and the (randomly placed) samples.",
+      "the lookups of a warp and served from shared memory / L2; DRAM carries the records' first touch, the (randomly placed) samples and two index-row segments per warp-group and chunk.",
       "", "Per-launch detail of that step:", ""]
 for (i, n), m in st:
     L.append(f"- #{i} `{n.split('(')[0].replace('void ', '')}`: {m['gpu__time_duration.sum']/1e3:.1f} us, DRAM read {m['dram__bytes_read.sum']/1e6:.0f} MB, write {m['dram__bytes_write.sum']/1e6:.0f} MB")

@@ -5,8 +5,13 @@
 //  * SORTED pipeline (-k 6, xs_gpu_lookup_samples) -- the fastest path, the bench headline:
 //      xs_sample_kernel / xs_locate_kernel        energy, material, UEG row, sort key, histogram
 //      radix sort (xs_sort.cuh)                   order by (material, energy)
-//      xs_sorted_kernel                           lane per lookup; the lookups of a warp share their
-//                                                 pair records (shared-memory ring, LDS broadcasts)
+//      xs_dense_kernel / xs_sorted_kernel         lane per lookup; the lookups of a warp share their
+//                                                 pair records (shared-memory ring, LDS broadcasts).
+//                                                 dense materials (many lookups per grid interval):
+//                                                 only the group's lowest / highest energy is
+//                                                 resolved, a lookup finds its record by comparing
+//                                                 its energy with the records' bounds; the others:
+//                                                 every lookup's record number is staged
 //  * SWEEP pipeline (-k 4/5, history mode) -- lookups grouped by material only:
 //      xs_sample_kernel / xs_history_step_kernel  energy, material, UEG row, histogram
 //      xs_partition_kernel                        group the lookups by material
@@ -774,9 +779,6 @@ XS_DEV PairRecord ldg_record(const double2 *rec)
     return r;
 }
 
-#ifndef XS_EXP
-#define XS_EXP 0
-#endif
 XS_DEV void record_step(const PairRecord &r, double e, double conc, double acc[5])
 {
     const double n = r.hi_e - e;
@@ -1249,7 +1251,6 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     bool ok[kPerLane];
 #pragma unroll
                     for (int w = 0; w < kPerLane; w++) { addr[w] = slot; ok[w] = true; }
-#if XS_EXP != 2      // (timing experiment 2: no selection)
                     if ((multi >> step) & 1u) {              // warp-uniform: more (or fewer) than one record
                         if ((two >> step) & 1u) {
                             // two records: one bound between them.  Nothing lies beyond the second
@@ -1285,7 +1286,6 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                             }
                         }
                     }
-#endif
                     PairRecord r = lds_record(addr[0]);
                     if (!ok[0]) resolve_own(r, e[0], where32[0], step);
                     record_step(r, e[0], conc, acc[0]);
