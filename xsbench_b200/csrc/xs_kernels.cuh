@@ -789,6 +789,78 @@ XS_DEV void record_step(const PairRecord &r, double e, double conc, double acc[5
     for (int k = 0; k < 5; k++) acc[k] += (r.hi[k] - f * r.dlt[k]) * conc;
 }
 
+// ---- shared by the two lane-per-lookup kernels (xs_sorted_kernel, xs_dense_kernel) ----
+
+// The segment (material) a warp-group belongs to: warp-uniform, <= 11 steps.
+XS_DEV int segment_of_group(const WindowArgs &A, int g, int sg = 0)
+{
+    while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;
+    return sg;
+}
+
+// A lane's kPerLane consecutive lookups of a group: energy and UEG row / hash bin.  Slots past
+// the end of the segment repeat the lookup in slot `idle_slot` (their results are dropped).
+// indirect: the sort's permutation is applied here instead of by a gather pass (two random reads
+// per lookup either way; -0.5 ms of gather kernel, +0.25 ms in here).
+XS_DEV void load_lane_samples(const WindowArgs &A, const WindowSegment &S, int first_in_seg, long idle_slot,
+                              double e[kPerLane], uint32_t where32[kPerLane], bool on[kPerLane])
+{
+#pragma unroll
+    for (int w = 0; w < kPerLane; w++) {
+        on[w] = first_in_seg + w < S.count;
+        const long t = on[w] ? S.offset + first_in_seg + w : idle_slot;
+        const long src = A.indirect ? (long)A.sample_id[t] : t;
+        if (A.indirect && A.pack) {
+            const double2 s = __ldg(A.pack + src);
+            e[w] = s.x;
+            where32[w] = (uint32_t)__double_as_longlong(s.y);
+        } else {
+            e[w] = A.energy[src];
+            where32[w] = A.where[src];
+        }
+    }
+}
+
+// A lane's finished lookups: argmax into the checksum, optional macro_xs dump, optional history
+// feedback n_forward = #{k : macro_xs[k] > 1.0} (openmp-threading/Simulation.c:225-228).
+XS_DEV void finish_lane_lookups(const WindowArgs &A, const BatchSink &sink, long t0, const bool on[kPerLane],
+                                const double acc[kPerLane][5], unsigned int &my_sum)
+{
+#pragma unroll
+    for (int w = 0; w < kPerLane; w++) {
+        if (!on[w]) continue;
+        double gap;
+        const int am = argmax5(acc[w], gap);
+        my_sum += (unsigned int)(am + 1);
+        if (sink.macro_out) {
+            const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
+#pragma unroll
+            for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[w][k];
+        }
+        if (sink.fwd_out) {
+            const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
+            int fwd = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) fwd += acc[w][k] > 1.0;
+            sink.fwd_out[id] = (unsigned char)fwd;
+        }
+    }
+}
+
+// Block's share of the verification sum, and (block 0) the lookups this launch completes.
+XS_DEV void finish_launch(const WindowArgs &A, const BatchSink &sink, unsigned int my_sum, unsigned long long *s_part)
+{
+    const unsigned long long bs = block_sum(my_sum, s_part);
+    if (threadIdx.x == 0) {
+        if (bs) atomicAdd(sink.accum, bs);
+        if (blockIdx.x == 0) {
+            unsigned long long done = 0;
+            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
+            atomicAdd(sink.accum + 1, done);
+        }
+    }
+}
+
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_SORTED_BLOCKS)
 xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
@@ -810,32 +882,16 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 
     // a block takes 8 consecutive groups: neighbouring energies share records in L1
     for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
-        int sg = 0;
-        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;      // warp-uniform, <= 11 steps
+        const int sg = segment_of_group(A, g);
         const WindowSegment &S = A.seg[sg];
         const int first_in_seg = (g - S.group_begin) * kSortedGroup + lane * kPerLane;
         const long t0 = S.offset + first_in_seg;
         double e[kPerLane];
         uint32_t where32[kPerLane];
         bool on[kPerLane];
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++) {
-            on[w] = first_in_seg + w < S.count;
-            // idle slots repeat the segment's last lookup (results dropped): the group's last
-            // lookup then still bounds the records of all the others
-            const long t = on[w] ? t0 + w : S.offset + S.count - 1;
-            // indirect: the sort's permutation is applied here instead of by a gather pass (two
-            // random reads per lookup either way; -0.5 ms of gather kernel, +0.25 ms in here)
-            const long src = A.indirect ? (long)A.sample_id[t] : t;
-            if (A.indirect && A.pack) {
-                const double2 s = __ldg(A.pack + src);
-                e[w] = s.x;
-                where32[w] = (uint32_t)__double_as_longlong(s.y);
-            } else {
-                e[w] = A.energy[src];
-                where32[w] = A.where[src];
-            }
-        }
+        // idle slots repeat the segment's last lookup: the group's last lookup then still bounds
+        // the records of all the others
+        load_lane_samples(A, S, first_in_seg, S.offset + S.count - 1, e, where32, on);
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
         const int ci = S.mat * kConcStride;
         double acc[kPerLane][5];
@@ -995,35 +1051,9 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             }
         }
 
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++) {
-            if (!on[w]) continue;
-            double gap;
-            const int am = argmax5(acc[w], gap);
-            my_sum += (unsigned int)(am + 1);
-            if (sink.macro_out) {
-                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
-#pragma unroll
-                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[w][k];
-            }
-            if (sink.fwd_out) {            // history mode feedback (openmp-threading/Simulation.c:225-228)
-                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
-                int fwd = 0;
-#pragma unroll
-                for (int k = 0; k < 5; k++) fwd += acc[w][k] > 1.0;
-                sink.fwd_out[id] = (unsigned char)fwd;
-            }
-        }
+        finish_lane_lookups(A, sink, t0, on, acc, my_sum);
     }
-    const unsigned long long bs = block_sum(my_sum, s_part);
-    if (threadIdx.x == 0) {
-        if (bs) atomicAdd(sink.accum, bs);
-        if (blockIdx.x == 0) {                               // lookups completed by this launch
-            unsigned long long done = 0;
-            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
-            atomicAdd(sink.accum + 1, done);
-        }
-    }
+    finish_launch(A, sink, my_sum, s_part);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1092,8 +1122,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     const uint32_t first_base = (uint32_t)__cvta_generic_to_shared(warp_first);
 
     for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
-        int sg = 0;
-        while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;      // warp-uniform, <= 11 steps
+        const int sg = segment_of_group(A, g);
         const WindowSegment &S = A.seg[sg];
         const int group_first = (g - S.group_begin) * kSortedGroup;
         const int first_in_seg = group_first + lane * kPerLane;
@@ -1101,21 +1130,8 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         double e[kPerLane];
         uint32_t where32[kPerLane];
         bool on[kPerLane];
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++) {
-            on[w] = first_in_seg + w < S.count;
-            // idle slots repeat the group's first lookup (results dropped)
-            const long t = on[w] ? t0 + w : S.offset + group_first;
-            const long src = A.indirect ? (long)A.sample_id[t] : t;
-            if (A.indirect && A.pack) {
-                const double2 s = __ldg(A.pack + src);
-                e[w] = s.x;
-                where32[w] = (uint32_t)__double_as_longlong(s.y);
-            } else {
-                e[w] = A.energy[src];
-                where32[w] = A.where[src];
-            }
-        }
+        // idle slots repeat the group's first lookup: they do not widen the group's energy range
+        load_lane_samples(A, S, first_in_seg, S.offset + group_first, e, where32, on);
         // The group's energy range.  Energies are non-negative doubles: their bit patterns order
         // like the values (and 64-bit integer compares run on the ALU pipe instead of queueing
         // behind the FP64 work).  The UEG row / hash bin is monotone in the energy, so the
@@ -1179,9 +1195,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         if (A.indirect && A.pack) {
             const int g2 = g + gridDim.x * kWarpsPerBlock;
             if (g2 < A.n_groups) {
-                int s2 = sg;
-                while (s2 + 1 < A.n_seg && g2 >= A.seg[s2 + 1].group_begin) s2++;
-                const WindowSegment &S2 = A.seg[s2];
+                const WindowSegment &S2 = A.seg[segment_of_group(A, g2, sg)];
                 const int first2 = (g2 - S2.group_begin) * kSortedGroup + lane * kPerLane;
                 next_any = true;
 #pragma unroll
@@ -1306,35 +1320,9 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             cp_async_wait_group<0>();
         }
 
-#pragma unroll
-        for (int w = 0; w < kPerLane; w++) {
-            if (!on[w]) continue;
-            double gap;
-            const int am = argmax5(acc[w], gap);
-            my_sum += (unsigned int)(am + 1);
-            if (sink.macro_out) {
-                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
-#pragma unroll
-                for (int k = 0; k < 5; k++) sink.macro_out[5 * id + k] = acc[w][k];
-            }
-            if (sink.fwd_out) {            // history mode feedback (openmp-threading/Simulation.c:225-228)
-                const long id = A.sample_id ? (long)A.sample_id[t0 + w] : t0 + w;
-                int fwd = 0;
-#pragma unroll
-                for (int k = 0; k < 5; k++) fwd += acc[w][k] > 1.0;
-                sink.fwd_out[id] = (unsigned char)fwd;
-            }
-        }
+        finish_lane_lookups(A, sink, t0, on, acc, my_sum);
     }
-    const unsigned long long bs = block_sum(my_sum, s_part);
-    if (threadIdx.x == 0) {
-        if (bs) atomicAdd(sink.accum, bs);
-        if (blockIdx.x == 0) {                               // lookups completed by this launch
-            unsigned long long done = 0;
-            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
-            atomicAdd(sink.accum + 1, done);
-        }
-    }
+    finish_launch(A, sink, my_sum, s_part);
 }
 
 // Per-nuclide bucket tables for nuclide-grid mode (init only): bucket[i][b] = number of grid
