@@ -157,6 +157,24 @@ def test_division_is_exact(small):
     assert np.array_equal(macro, omacro)
 
 
+def test_lookups_on_grid_points_only(small):
+    """Every lookup energy IS a grid point of one of the first nuclides, in every material: each
+    lookup sits exactly ON an interval bound of some nuclide, where "<" and "<=" part ways (and
+    where the reference's hash-grid guards `E <= e_low` / `E >= e_high`, cuda/Simulation.cu:150-156,
+    come into play).  The dense kernel sends such a lookup through the reference's own procedure;
+    results must equal the oracle's bit for bit on every grid type."""
+    n_gp = 1000
+    grid_e = small.oracle.nuclide_grid[0::6]
+    e1 = np.concatenate([grid_e[j * n_gp:(j + 1) * n_gp] for j in range(4)])
+    e1 = e1[(e1 >= 0) & (e1 < 1)]
+    e = np.tile(e1, 12)
+    m = np.repeat(np.arange(12, dtype=np.int32), len(e1))
+    res, macro = small.gpu.lookup_samples(e, m, want_macro_xs=True)
+    v, omacro = small.oracle.lookup_samples(e, m)
+    assert res.verification == v and res.n_lookups == len(e)
+    assert np.array_equal(macro, omacro)
+
+
 @pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1000])
 def test_lookup_samples_ragged_sizes(small, n):
     rng = np.random.default_rng(n)
