@@ -90,6 +90,7 @@ struct DeviceState {
     unsigned long long *accum = nullptr;   // device [2]
     unsigned int *counters = nullptr;      // device [kNumCounters]
     unsigned int *histogram = nullptr;     // device [16]
+    unsigned int *dense_counter = nullptr; // lane-per-lookup kernels: [0] next warp-group, [1] warps done (the kernel re-arms both)
     unsigned long long *h_accum = nullptr; // pinned host [2]
     unsigned int *h_hist = nullptr;        // pinned host [16]
     int h_mat_first[XS_NUM_MATERIALS + 1] = {};
@@ -369,6 +370,8 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     CUDA_TRY(cudaMalloc(&d.accum, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&d.counters, kNumCounters * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&d.histogram, kNumHist * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&d.dense_counter, 2 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(d.dense_counter, 0, 2 * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreateWithFlags(&d.ev_copy[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming));
@@ -533,7 +536,8 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
             sgm.offset = b.offset[m];
             sgm.count = (int)b.count[m];
             sgm.group_begin = (int)groups;
-            groups += (b.count[m] + xs::kSortedGroup - 1) / xs::kSortedGroup;
+            const int group = dense ? xs::kDenseGroup : xs::kSortedGroup;
+            groups += (b.count[m] + group - 1) / group;
         }
         if (groups == 0) continue;
         a.n_groups = (int)groups;
@@ -556,7 +560,9 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
         if (rc != XS_OK) return rc;
         const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
         if (blocks > max_useful) blocks = (int)max_useful;
-        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink);
+        xs::BatchSink launch_sink = sink;
+        launch_sink.batch_counter = d.dense_counter;          // group hand-out; the kernel leaves it zeroed
+        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, launch_sink);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
     }
@@ -1341,7 +1347,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         if (d.stream) cudaStreamSynchronize(d.stream);
         cudaFree(d.hot_slab); cudaFree(d.index_grid); cudaFree(d.grid);
         cudaFree(d.mat_first); cudaFree(d.mat_nuc); cudaFree(d.mat_conc);
-        cudaFree(d.accum); cudaFree(d.counters); cudaFree(d.histogram);
+        cudaFree(d.accum); cudaFree(d.counters); cudaFree(d.histogram); cudaFree(d.dense_counter);
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         cudaFree(d.bin_count); cudaFree(d.bin_chunk_sum);

@@ -798,15 +798,38 @@ XS_DEV int segment_of_group(const WindowArgs &A, int g, int sg = 0)
     return sg;
 }
 
-// A lane's kPerLane consecutive lookups of a group: energy and UEG row / hash bin.  Slots past
+// Warp-groups are handed out by an atomic counter, in order: fuel (321 steps per group) comes
+// first, the cheap materials fill the tail.  A static split leaves 16-vs-15 fuel groups per warp
+// and cost 12 % of the kernel.  sink.batch_counter: [0] next group, [1] warps that are done -- the
+// last warp of a launch re-arms both, so launches on one stream share the two words.
+XS_DEV int warp_next_group(const BatchSink &sink, int lane)
+{
+    int v = 0;
+    if (lane == 0) v = (int)atomicAdd(sink.batch_counter, 1u);
+    return __shfl_sync(kFullMask, v, 0);
+}
+XS_DEV void warp_groups_done(const BatchSink &sink, int lane)
+{
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(sink.batch_counter + 1, 1u) == gridDim.x * kWarpsPerBlock - 1) {
+            sink.batch_counter[0] = 0;
+            sink.batch_counter[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// A lane's PL consecutive lookups of a group: energy and UEG row / hash bin.  Slots past
 // the end of the segment repeat the lookup in slot `idle_slot` (their results are dropped).
 // indirect: the sort's permutation is applied here instead of by a gather pass (two random reads
 // per lookup either way; -0.5 ms of gather kernel, +0.25 ms in here).
+template <int PL>
 XS_DEV void load_lane_samples(const WindowArgs &A, const WindowSegment &S, int first_in_seg, long idle_slot,
-                              double e[kPerLane], uint32_t where32[kPerLane], bool on[kPerLane])
+                              double e[PL], uint32_t where32[PL], bool on[PL])
 {
 #pragma unroll
-    for (int w = 0; w < kPerLane; w++) {
+    for (int w = 0; w < PL; w++) {
         on[w] = first_in_seg + w < S.count;
         const long t = on[w] ? S.offset + first_in_seg + w : idle_slot;
         const long src = A.indirect ? (long)A.sample_id[t] : t;
@@ -823,11 +846,12 @@ XS_DEV void load_lane_samples(const WindowArgs &A, const WindowSegment &S, int f
 
 // A lane's finished lookups: argmax into the checksum, optional macro_xs dump, optional history
 // feedback n_forward = #{k : macro_xs[k] > 1.0} (openmp-threading/Simulation.c:225-228).
-XS_DEV void finish_lane_lookups(const WindowArgs &A, const BatchSink &sink, long t0, const bool on[kPerLane],
-                                const double acc[kPerLane][5], unsigned int &my_sum)
+template <int PL>
+XS_DEV void finish_lane_lookups(const WindowArgs &A, const BatchSink &sink, long t0, const bool on[PL],
+                                const double acc[PL][5], unsigned int &my_sum)
 {
 #pragma unroll
-    for (int w = 0; w < kPerLane; w++) {
+    for (int w = 0; w < PL; w++) {
         if (!on[w]) continue;
         double gap;
         const int am = argmax5(acc[w], gap);
@@ -880,8 +904,8 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     const uint32_t *first_rec = warp_rec;                                        // lookup 0 of the group
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + (kStaged ? warp * kRingBytes : 0);
 
-    // a block takes 8 consecutive groups: neighbouring energies share records in L1
-    for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
+    // groups are handed out in order by an atomic counter (see warp_next_group)
+    for (int g = warp_next_group(sink, lane); g < A.n_groups; g = warp_next_group(sink, lane)) {
         const int sg = segment_of_group(A, g);
         const WindowSegment &S = A.seg[sg];
         const int first_in_seg = (g - S.group_begin) * kSortedGroup + lane * kPerLane;
@@ -891,7 +915,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         bool on[kPerLane];
         // idle slots repeat the segment's last lookup: the group's last lookup then still bounds
         // the records of all the others
-        load_lane_samples(A, S, first_in_seg, S.offset + S.count - 1, e, where32, on);
+        load_lane_samples<kPerLane>(A, S, first_in_seg, S.offset + S.count - 1, e, where32, on);
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
         const int ci = S.mat * kConcStride;
         double acc[kPerLane][5];
@@ -1051,8 +1075,9 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             }
         }
 
-        finish_lane_lookups(A, sink, t0, on, acc, my_sum);
+        finish_lane_lookups<kPerLane>(A, sink, t0, on, acc, my_sum);
     }
+    warp_groups_done(sink, lane);
     finish_launch(A, sink, my_sum, s_part);
 }
 
@@ -1084,6 +1109,11 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 #ifndef XS_DENSE_SPAN
 #define XS_DENSE_SPAN 4
 #endif
+#ifndef XS_DENSE_PER_LANE
+#define XS_DENSE_PER_LANE 3          // measured (lookup phase of -k 6, large): 2 -> 2.35 ms, 3 -> 2.21, 4 -> 2.26
+#endif
+constexpr int kDensePerLane = XS_DENSE_PER_LANE;       // consecutive lookups per lane
+constexpr int kDenseGroup = 32 * kDensePerLane;        // lookups per warp-group
 constexpr int kDenseRing = XS_DENSE_RING;              // steps of records in flight per warp (a power of two)
 constexpr int kDenseSpan = XS_DENSE_SPAN;              // records per ring slot (2..4)
 constexpr int kDenseSlotBytes = kDenseSpan * 128;
@@ -1121,17 +1151,19 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + warp * kDenseRingBytes;
     const uint32_t first_base = (uint32_t)__cvta_generic_to_shared(warp_first);
 
-    for (int g = blockIdx.x * kWarpsPerBlock + warp; g < A.n_groups; g += gridDim.x * kWarpsPerBlock) {
+    int g = warp_next_group(sink, lane);
+    while (g < A.n_groups) {
+        const int g_next = warp_next_group(sink, lane);      // (known early: its samples are requested below)
         const int sg = segment_of_group(A, g);
         const WindowSegment &S = A.seg[sg];
-        const int group_first = (g - S.group_begin) * kSortedGroup;
-        const int first_in_seg = group_first + lane * kPerLane;
+        const int group_first = (g - S.group_begin) * kDenseGroup;
+        const int first_in_seg = group_first + lane * kDensePerLane;
         const long t0 = S.offset + first_in_seg;
-        double e[kPerLane];
-        uint32_t where32[kPerLane];
-        bool on[kPerLane];
+        double e[kDensePerLane];
+        uint32_t where32[kDensePerLane];
+        bool on[kDensePerLane];
         // idle slots repeat the group's first lookup: they do not widen the group's energy range
-        load_lane_samples(A, S, first_in_seg, S.offset + group_first, e, where32, on);
+        load_lane_samples<kDensePerLane>(A, S, first_in_seg, S.offset + group_first, e, where32, on);
         // The group's energy range.  Energies are non-negative doubles: their bit patterns order
         // like the values (and 64-bit integer compares run on the ALU pipe instead of queueing
         // behind the FP64 work).  The UEG row / hash bin is monotone in the energy, so the
@@ -1139,7 +1171,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         long long eb_min = __double_as_longlong(e[0]), eb_max = eb_min;
         uint32_t where_min = where32[0], where_max = where32[0];
 #pragma unroll
-        for (int w = 1; w < kPerLane; w++) {
+        for (int w = 1; w < kDensePerLane; w++) {
             eb_min = min(eb_min, __double_as_longlong(e[w]));
             eb_max = max(eb_max, __double_as_longlong(e[w]));
             where_min = min(where_min, where32[w]);
@@ -1156,9 +1188,9 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
         const int ci = S.mat * kConcStride;
-        double acc[kPerLane][5];
+        double acc[kDensePerLane][5];
 #pragma unroll
-        for (int w = 0; w < kPerLane; w++)
+        for (int w = 0; w < kDensePerLane; w++)
 #pragma unroll
             for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
 
@@ -1190,16 +1222,16 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         };
         // The warp's next group: fetch its sample ids now, request the samples behind them after
         // the first chunk (two dependent random reads otherwise wait in front of every group).
-        uint32_t next_id[kPerLane];
+        uint32_t next_id[kDensePerLane];
         bool next_any = false;
         if (A.indirect && A.pack) {
-            const int g2 = g + gridDim.x * kWarpsPerBlock;
+            const int g2 = g_next;
             if (g2 < A.n_groups) {
                 const WindowSegment &S2 = A.seg[segment_of_group(A, g2, sg)];
-                const int first2 = (g2 - S2.group_begin) * kSortedGroup + lane * kPerLane;
+                const int first2 = (g2 - S2.group_begin) * kDenseGroup + lane * kDensePerLane;
                 next_any = true;
 #pragma unroll
-                for (int w = 0; w < kPerLane; w++)
+                for (int w = 0; w < kDensePerLane; w++)
                     next_id[w] = A.sample_id[S2.offset + min(first2 + w, S2.count - 1)];
             }
         }
@@ -1210,7 +1242,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             if (c0 == 32 || (c0 == 0 && n_nuc <= 32)) {
                 if (next_any) {
 #pragma unroll
-                    for (int w = 0; w < kPerLane; w++) prefetch_l2(A.pack + next_id[w]);
+                    for (int w = 0; w < kDensePerLane; w++) prefetch_l2(A.pack + next_id[w]);
                 }
             }
             const uint32_t multi = multi_next, two = two_next;   // known a chunk ahead, in registers: no load in front of the branches
@@ -1261,17 +1293,17 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     const double conc = c_conc_pad[conc_base + step];
                     const uint32_t slot = ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes);
                     // which ring record each of the lane's lookups uses, and whether that is settled
-                    uint32_t addr[kPerLane];
-                    bool ok[kPerLane];
+                    uint32_t addr[kDensePerLane];
+                    bool ok[kDensePerLane];
 #pragma unroll
-                    for (int w = 0; w < kPerLane; w++) { addr[w] = slot; ok[w] = true; }
+                    for (int w = 0; w < kDensePerLane; w++) { addr[w] = slot; ok[w] = true; }
                     if ((multi >> step) & 1u) {              // warp-uniform: more (or fewer) than one record
                         if ((two >> step) & 1u) {
                             // two records: one bound between them.  Nothing lies beyond the second
                             // (the search is monotone); ON the bound the reference decides.
                             const long long hi0 = lds_s64(slot + 96);
 #pragma unroll
-                            for (int w = 0; w < kPerLane; w++) {
+                            for (int w = 0; w < kDensePerLane; w++) {
                                 const long long eb = __double_as_longlong(e[w]);
                                 addr[w] = slot + (eb > hi0 ? 128u : 0u);
                                 ok[w] = eb != hi0;
@@ -1285,7 +1317,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                             for (int i = 0; i < kDenseSpan; i++) hi[i] = lds_s64(slot + i * 128 + 96);
                             const uint32_t n_ring = min(lds_v2_u32(first_addr + step * 8).y & 0xffffu, (uint32_t)kDenseSpan);
 #pragma unroll
-                            for (int w = 0; w < kPerLane; w++) {
+                            for (int w = 0; w < kDensePerLane; w++) {
                                 const long long eb = __double_as_longlong(e[w]);
                                 uint32_t which = 0;
                                 bool beyond = true, on_bound = false;
@@ -1304,7 +1336,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                     if (!ok[0]) resolve_own(r, e[0], where32[0], step);
                     record_step(r, e[0], conc, acc[0]);
 #pragma unroll
-                    for (int w = 1; w < kPerLane; w++) {
+                    for (int w = 1; w < kDensePerLane; w++) {
                         if (addr[w] != addr[w - 1] || !ok[w] || !ok[w - 1]) {
                             r = lds_record(addr[w]);
                             if (!ok[w]) resolve_own(r, e[w], where32[w], step);
@@ -1320,8 +1352,10 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
             cp_async_wait_group<0>();
         }
 
-        finish_lane_lookups(A, sink, t0, on, acc, my_sum);
+        finish_lane_lookups<kDensePerLane>(A, sink, t0, on, acc, my_sum);
+        g = g_next;
     }
+    warp_groups_done(sink, lane);
     finish_launch(A, sink, my_sum, s_part);
 }
 
