@@ -146,7 +146,7 @@ struct xs_gpu_ctx {
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
-    int dense_min = 32;                    // -k 6: materials with >= this many lookups per grid interval go to xs_dense_kernel (0 = never)
+    int dense_min = 64;                    // -k 6: materials with >= this many lookups per grid interval go to xs_dense_kernel (0 = never)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
     size_t smem_bytes = 0;
@@ -1031,7 +1031,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->fuse_gather = env_int("XSB200_FUSE_GATHER", 1);
     ctx->pack_samples = env_int("XSB200_PACK_SAMPLES", 1);
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
-    ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 32));
+    ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);
