@@ -517,7 +517,7 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
 }
 
 // Lane-per-lookup sweep over a batch sorted by (material, energy): the materials with many lookups
-// per grid interval (>= ctx->dense_min: a warp-group's 64 lookups then fall into the first lookup's
+// per grid interval (>= ctx->dense_min: a warp-group's 96 lookups then fall into the first lookup's
 // interval or the next) go to xs_dense_kernel, the others to xs_sorted_kernel -- two launches.
 int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::BatchSink sink)
 {

@@ -1083,11 +1083,11 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 
 // ---------------------------------------------------------------------------------------
 // xs_dense_kernel -- the sorted kernel for DENSE segments (many lookups per grid interval:
-// large/fuel has 209).  The 64 energy-sorted lookups of a warp-group then fall, per nuclide,
-// into ONE grid interval (73 % of the steps of large/fuel) or a few consecutive ones.  So only
+// large/fuel has 209).  The 96 energy-sorted lookups of a warp-group (3 per lane) then fall, per
+// nuclide, into ONE grid interval (63 % of the steps of large/fuel) or a few consecutive ones.  So only
 // the group's lowest and highest energy are resolved (lane l resolves nuclide c0 + l: two
-// index-row segments per group and chunk instead of 64, or two bucket-table searches per nuclide
-// instead of 64 in hash / nuclide mode), which gives, per nuclide, the first record k_min and
+// index-row segments per group and chunk instead of 96, or two bucket-table searches per nuclide
+// instead of 96 in hash / nuclide mode), which gives, per nuclide, the first record k_min and
 // the number of records n = k_max - k_min + 1 the group can touch (the search is monotone in
 // the energy).  n records (at most kDenseSpan) go through the shared-memory ring.
 //   n == 1: every lookup of the group uses that record -- no per-lookup work at all;
@@ -1097,7 +1097,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 //           the reference's procedure (nuclide_low).
 // Results therefore never depend on how well the batch is sorted: min / max are taken over the
 // group, not assumed from positions.  The next chunk is resolved (and its records requested
-// into L2) before the current one is gathered: no staging phase, no transposition, 1/32 of the
+// into L2) before the current one is gathered: no staging phase, no transposition, 1/48 of the
 // index-grid traffic of xs_sorted_kernel.
 // ---------------------------------------------------------------------------------------
 #ifndef XS_DENSE_BLOCKS
