@@ -72,6 +72,7 @@ def main():
         (68, 11303, 2, 10000, 1, 34, 10000),
         (355, 1000, 2, 2000, 1, 34, 3000),
         (355, 1000, 0, 10000, 1, 7, 5000),
+        (355, 11303, 2, 10000, 2, 100000, 0),      # the canonical grid size (hash grid: same sums, fast to build)
     ]:
         v = checksum(n_iso, n_gp, gt, hb, method, lookups, particles)
         out["checksums"].append({"n_isotopes": n_iso, "n_gridpoints": n_gp, "grid_type": gt, "hash_bins": hb,
@@ -82,7 +83,7 @@ def main():
     # per-lookup macro_xs vectors
     ids = list(range(0, 64)) + [1000, 4097, 99999, 1234567, 16999999, 2**30 - 1]
     for (n_iso, n_gp, gt, hb) in [(68, 1000, 0, 10000), (68, 1000, 2, 500), (68, 1000, 1, 10000),
-                                  (355, 1000, 0, 10000), (68, 11303, 0, 10000)]:
+                                  (355, 1000, 0, 10000), (68, 11303, 0, 10000), (355, 11303, 2, 10000)]:
         out["lookups"].append({"n_isotopes": n_iso, "n_gridpoints": n_gp, "grid_type": gt, "hash_bins": hb,
                                "rows": per_lookup_vectors(n_iso, n_gp, gt, hb, ids)})
         print("vectors", n_iso, n_gp, gt)

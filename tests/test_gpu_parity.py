@@ -540,3 +540,175 @@ def test_billion_lookups_bounded_passes():
         a = gpu.run_range(0, 400_000_000, inp).verification + gpu.run_range(400_000_000, 600_000_000, inp).verification
         assert a == res.verification
     xs.free_simulation_data(mats)
+
+
+# ---- two live contexts on one device keep their own material tables ------------------------------------
+def test_two_live_contexts_do_not_clobber_each_other():
+    """Round 1 kept the zero-padded concentrations in a process-global __constant__ symbol that every
+    xs_gpu_init overwrote: with a 68-nuclide and a 355-nuclide context alive together the older one
+    silently multiplied by the newer one's concentrations on the -k 4/5/6 / host-sample paths.  The
+    table is a kernel parameter now; both contexts must keep giving their single-context results
+    whatever the order of creation and use."""
+    rng = np.random.default_rng(23)
+    e = rng.random(60_000); m = rng.integers(0, 12, len(e)).astype(np.int32)
+    a = Problem("small", 1000, "unionized", 500, method="event", lookups=100000)
+    want_a = a.oracle.lookup_samples(e, m)
+    b = Problem("large", 1000, "unionized", 500, method="event", lookups=100000)     # created while `a` is alive
+    want_b = b.oracle.lookup_samples(e, m)
+    try:
+        for _ in range(2):
+            for p, (want_v, want_macro), golden, size in ((a, want_a, 302880, "small"), (b, want_b, 303045, "large")):
+                for k in (4, 5, 6):
+                    inp = xs.make_inputs(size=size, grid="unionized", gridpoints=1000, hash_bins=500, method="event",
+                                         lookups=100000, kernel_id=k)
+                    assert p.gpu.run(inp).verification == golden, (size, k)
+                res, macro = p.gpu.lookup_samples(e, m, want_macro_xs=True)
+                assert res.verification == want_v and np.array_equal(macro, want_macro), size
+        # and a third context of the first size, created last, does not disturb the second
+        c = Problem("small", 1000, "hash", 500, method="event", lookups=100000)
+        try:
+            res, macro = b.gpu.lookup_samples(e, m, want_macro_xs=True)
+            assert res.verification == want_b[0] and np.array_equal(macro, want_b[1])
+            res, macro = c.gpu.lookup_samples(e, m, want_macro_xs=True)
+            assert res.verification == want_a[0] and np.array_equal(macro, want_a[1])
+        finally:
+            c.close()
+    finally:
+        a.close(); b.close()
+
+
+# ---- host samples are validated, not trusted ---------------------------------------------------------------
+@pytest.mark.parametrize("bad_e,bad_m", [(0.5, 12), (0.5, -1), (0.5, 1 << 20), (-1e-9, 3), (1.0000001, 3), (float("nan"), 3),
+                                          (float("inf"), 0), (-float("inf"), 11)])
+def test_lookup_samples_rejects_bad_samples(small, bad_e, bad_m):
+    """A material outside [0, 12) or an energy outside [0, 1] is XS_ERR_ARG (include/xs_gpu.h), not an
+    out-of-bounds access; the context stays usable afterwards."""
+    rng = np.random.default_rng(1)
+    e = rng.random(5000); m = rng.integers(0, 12, len(e)).astype(np.int32)
+    good, _ = small.gpu.lookup_samples(e, m)
+    e2, m2 = e.copy(), m.copy()
+    e2[1234], m2[1234] = bad_e, bad_m
+    with pytest.raises(xs.XSGpuError) as ei:
+        small.gpu.lookup_samples(e2, m2, want_macro_xs=True)
+    assert ei.value.code == _abi.XS_ERR_ARG
+    again, _ = small.gpu.lookup_samples(e, m)
+    assert again.verification == good.verification and again.n_lookups == len(e)
+    edge, _ = small.gpu.lookup_samples(np.array([0.0, 1.0]), np.array([0, 11], np.int32))     # the closed ends are fine
+    assert edge.n_lookups == 2
+
+
+# ---- per-lookup parity at the canonical grid size (355 x 11,303) ---------------------------------------
+@pytest.fixture(scope="module")
+def canonical_samples():
+    """The fuel lookups (all 2.36 M: 209 per grid interval, the density xs_dense_kernel is built for)
+    and every fourth of the others of the canonical 17 M-lookup stream, with the oracle's macro_xs
+    for them.  The oracle works on the hash grid (200 MB; macro_xs is grid-type invariant bit for
+    bit: tests/test_oracle.py::test_macro_xs_bit_identical_to_reference)."""
+    n = 17_000_000
+    e = np.empty(n); m = np.empty(n, np.int32)
+    ol.oracle().xo_sample(0, n, e.ctypes.data, m.ctypes.data)
+    keep = (m == 0) | (np.arange(n) % 4 == 0)
+    e, m = e[keep].copy(), m[keep].copy()
+    orc = ol.OracleProblem(355, 11303, 2, 10000)
+    v, macro = orc.lookup_samples(e, m, nthreads=NTHREADS)
+    orc.close()
+    return e, m, v, macro
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("grid", ["unionized", "hash", "nuclide"])
+def test_canonical_grid_per_lookup_parity(canonical_samples, grid):
+    """-k 6 pipeline (xs_gpu_lookup_samples: sort + xs_dense_kernel for fuel and the other dense
+    materials + xs_sorted_kernel for the rest) on the REAL problem size: 355 nuclides x 11,303 grid
+    points, fuel at its real density (11-chunk nuclide loop, index-row prefetch of the chunk after
+    next, 4-record rings).  6 M lookups, every macro_xs vector compared bit for bit with the oracle,
+    plus the committed reference rows of this grid size."""
+    e, m, v, omacro = canonical_samples
+    inp = xs.make_inputs(size="large", method="event", grid=grid, kernel_id=6)
+    assert (inp.n_isotopes, inp.n_gridpoints) == (355, 11303)
+    mats = xs.materials_only(inp)                       # device-side generator: byte-identical to the host's
+    with xs.move_simulation_data_to_device(inp, mats) as gpu:
+        assert np.count_nonzero(m == 0) >= 64 * 11303   # fuel is dense at this count
+        res, macro = gpu.lookup_samples(e, m, want_macro_xs=True)
+        assert res.n_lookups == len(e) and res.verification == v
+        assert np.array_equal(macro, omacro)
+        rows = [g for g in GOLDEN["lookups"] if (g["n_isotopes"], g["n_gridpoints"]) == (355, 11303)]
+        assert rows
+        for row in rows[0]["rows"]:
+            ge, gm, gx, ga = gpu.dump(row["id"], 1)
+            assert ge[0] == float.fromhex(row["energy"]) and gm[0] == row["mat"] and ga[0] == row["argmax"]
+            assert max_rel(gx[0], unhex(row["macro_xs"])) <= REL_TOL
+            r1, x1 = gpu.lookup_samples(ge, gm, want_macro_xs=True)          # sweep path: reference order
+            assert np.array_equal(x1[0], unhex(row["macro_xs"]))
+        assert gpu.run_range(0, 100000, xs.make_inputs(size="large", method="event", grid=grid, kernel_id=6, lookups=100000)).verification == 298914
+    xs.free_simulation_data(mats)
+
+
+def test_small_canonical_grid_golden_rows():
+    """The committed reference rows for 68 x 11,303 (tests/golden/reference_vectors.json) on the GPU."""
+    rows = [g for g in GOLDEN["lookups"] if (g["n_isotopes"], g["n_gridpoints"]) == (68, 11303)]
+    assert rows
+    inp = xs.make_inputs(size="small", method="event", grid="unionized", kernel_id=6)
+    mats = xs.materials_only(inp)
+    with xs.move_simulation_data_to_device(inp, mats) as gpu:
+        for row in rows[0]["rows"]:
+            ge, gm, gx, ga = gpu.dump(row["id"], 1)
+            assert ge[0] == float.fromhex(row["energy"]) and gm[0] == row["mat"] and ga[0] == row["argmax"]
+            assert max_rel(gx[0], unhex(row["macro_xs"])) <= REL_TOL
+            _, x1 = gpu.lookup_samples(ge, gm, want_macro_xs=True)
+            assert np.array_equal(x1[0], unhex(row["macro_xs"]))
+    xs.free_simulation_data(mats)
+
+
+# ---- the host driver binary: exit status = checksum validity (the reference's only test) ---------------
+XSBENCH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "xsbench_b200", "xsbench")
+
+
+def run_xsbench(args, cwd=None):
+    import subprocess
+    p = subprocess.run([XSBENCH] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    return p.returncode, p.stdout
+
+
+@pytest.mark.parametrize("args,checksum", [
+    (["-s", "small", "-m", "event", "-k", "0"], 945990),
+    (["-s", "small", "-m", "event", "-k", "6"], 945990),
+    (["-s", "small", "-m", "event", "-k", "4", "-G", "hash"], 945990),
+    (["-s", "small", "-m", "event", "-k", "6", "-G", "nuclide"], 945990),
+    (["-s", "small", "-m", "history"], 941535),
+    (["-s", "small", "-m", "event", "-k", "6", "--device-init"], 945990),
+])
+def test_xsbench_binary_exit_status(args, checksum):
+    """openmp-threading/Main.c:112,122 + .github/workflows/omp.yml:20-27: the reference is tested by
+    running the binary on a table configuration and checking its exit status.  Same here, on the GPU."""
+    rc, out = run_xsbench(args + ["-t", str(NTHREADS)])
+    assert rc == 0, out[-2000:]
+    assert f"Verification checksum: {checksum} (Valid)" in out
+
+
+def test_xsbench_binary_reports_invalid_and_errors():
+    rc, out = run_xsbench(["-s", "small", "-m", "event", "-l", "12345", "-g", "300"])     # not in the table
+    assert rc == 1 and "WARNING - INVALID CHECKSUM" in out
+    rc, out = run_xsbench(["-s", "small", "-m", "event", "-k", "9", "-g", "300"])
+    assert rc != 0 and "No kernel ID 9" in out
+    rc, out = run_xsbench(["-s", "nonsense"])
+    assert rc == 4                                                                       # usage error (cuda/io.cu:208-224)
+
+
+@pytest.mark.parametrize("grid", ["unionized", "hash"])
+def test_xsbench_binary_write_then_read(tmp_path, grid):
+    """-b write, then -b read in the same directory (cuda/io.cu:443-495): the problem loaded from
+    XS_data.dat gives the same (valid) checksum as the generated one; so does a file written from a
+    problem that was generated on the device."""
+    base = ["-s", "small", "-m", "event", "-G", grid, "-k", "6", "-l", "100000", "-t", str(NTHREADS)]
+    rc, out = run_xsbench(base + ["-b", "write"], cwd=tmp_path)
+    assert rc == 0 and "Verification checksum: 299541 (Valid)" in out, out[-1500:]
+    first = open(tmp_path / "XS_data.dat", "rb").read()
+    rc, out = run_xsbench(base + ["-b", "read"], cwd=tmp_path)
+    assert rc == 0 and "Reading all data structures from binary file" in out
+    assert "Verification checksum: 299541 (Valid)" in out
+    rc, out = run_xsbench(base + ["-b", "write", "--device-init"], cwd=tmp_path)
+    assert rc == 0, out[-1500:]
+    assert open(tmp_path / "XS_data.dat", "rb").read() == first                         # byte-identical generator
+    rc, out = run_xsbench(["-s", "small", "-m", "history", "-G", grid, "-p", "3000", "-b", "read"], cwd=tmp_path)
+    assert "Verification checksum:" in out and rc in (0, 1)

@@ -293,3 +293,66 @@ def test_binary_roundtrip(tmp_path):
         xs.free_simulation_data(sd); xs.free_simulation_data(back)
     finally:
         os.chdir(exe_cwd)
+
+
+def test_binary_read_accepts_reference_files(tmp_path):
+    """`-b read` falls back to the reference's own format when the header magic is absent: a raw
+    SimulationData dump (128 bytes for the cuda/ port, 112 for openmp-threading; stale pointers
+    included) followed by the six arrays (cuda/io.cu:443-495)."""
+    import ctypes as C
+    exe_cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        lib = _abi.host_lib()
+        for argv in (["-s", "small", "-g", "150", "-G", "unionized"], ["-s", "small", "-g", "150", "-G", "hash", "-h", "40"],
+                     ["-s", "small", "-g", "150", "-G", "nuclide"]):
+            inp = xs.read_CLI(argv)
+            sd = xs.grid_init_do_not_profile(inp)
+            a = xs.simulation_arrays(inp, sd)
+            for struct_bytes in (128, 112):
+                raw = bytes(sd)                              # our struct is laid out like the cuda/ port's (128 bytes)
+                assert len(raw) == 128
+                with open("XS_data.dat", "wb") as f:
+                    f.write(raw[:80] + b"\xaa" * (struct_bytes - 80))      # shared prefix + that port's stale tail
+                    for k in ("num_nucs", "concs", "mats", "nuclide_grid", "index_grid", "unionized_energy_array"):
+                        f.write(a[k].tobytes())
+                back = lib.binary_read(inp)
+                b = xs.simulation_arrays(inp, back)
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), (argv, struct_bytes, k)
+                assert back.max_num_nucs == sd.max_num_nucs
+                xs.free_simulation_data(back)
+            xs.free_simulation_data(sd)
+    finally:
+        os.chdir(exe_cwd)
+
+
+def test_binary_read_of_a_file_the_reference_wrote(tmp_path):
+    """The unmodified reference (openmp-threading, oracle/_ref/XSBench_ref) writes XS_data.dat; our
+    binary_read loads it and the arrays equal our own generator's."""
+    import subprocess
+    import oracle_lib as ol
+    if not os.path.exists(ol.REF_BIN):
+        pytest.skip("oracle/_ref/XSBench_ref not built")
+    exe_cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        subprocess.run([ol.REF_BIN, "-s", "small", "-g", "120", "-m", "event", "-l", "100", "-b", "write", "-t", "2"],
+                       check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
+        assert os.path.exists("XS_data.dat")
+        inp = xs.read_CLI(["-s", "small", "-g", "120"])
+        back = _abi.host_lib().binary_read(inp)
+        sd = xs.grid_init_do_not_profile(inp)
+        a, b = xs.simulation_arrays(inp, sd), xs.simulation_arrays(inp, back)
+        assert back.max_num_nucs == sd.max_num_nucs
+        w = sd.max_num_nucs
+        # (the reference leaves the unused tail of every material's row uninitialised)
+        valid = np.concatenate([np.arange(m * w, m * w + a["num_nucs"][m]) for m in range(12)])
+        for k in a:
+            if k in ("concs", "mats"):
+                assert np.array_equal(a[k][valid], b[k][valid]), k
+            else:
+                assert np.array_equal(a[k], b[k]), k
+        xs.free_simulation_data(sd); xs.free_simulation_data(back)
+    finally:
+        os.chdir(exe_cwd)

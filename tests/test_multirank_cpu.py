@@ -27,6 +27,11 @@ def _worker(rank, world, port, mode, total, q):
         first, count = sharding.weak_shard(total, rank, world)
     v = p.event(first, count, 1)
     tv, tn = sharding.allreduce_result(v, count)
+    # bench.py's per-step collective (asynchronous submit, one waiting read), twice over like two steps
+    red = sharding.ResultReducer()
+    red.submit(1, 2)
+    red.submit(v, count)
+    assert red.result() == (tv, tn)
     q.put((rank, first, count, tv, tn))
     dist.destroy_process_group()
 
@@ -64,6 +69,9 @@ def test_shard_helpers():
     with pytest.raises(ValueError):
         sharding.strong_shard(10, 2, 2)
     assert sharding.allreduce_result(5, 6) == (5, 6)                       # no group: identity
+    red = sharding.ResultReducer()
+    red.submit(7, 8)
+    assert red.result() == (7, 8)
 
 
 def test_bench_reference_arm_only_rank0_prints():

@@ -181,6 +181,25 @@ def test_event_and_history_match_reference_drivers():
         assert r.run_history_based_simulation(inp_h, sd, 1) == p.history(0, 2000, 13, NTHREADS)
 
 
+@needs_ref
+@pytest.mark.parametrize("n_iso,n_gp,gt,hb,lookups", [(68, 800, 0, 10000, 30000), (68, 800, 2, 200, 30000),
+                                                        (68, 800, 1, 10000, 20000), (355, 300, 0, 10000, 25000)])
+def test_reference_sorted_variant_matches_oracle(n_iso, n_gp, gt, hb, lookups):
+    """the reference's CPU "-k 1" (sample, key-value quicksort by material, per-material
+    quicksort by energy, 12 sorted loops: openmp-threading/Simulation.c:698-871 with the sorts of :565-679)
+    run unmodified from libxsref.so.  The verification sum does not depend on the order of the lookups, so
+    it must equal the reference's own unsorted driver and the oracle -- which is what pins the hash of the
+    GPU's sorted pipeline (-k 6) to the reference's sorted path, not only to its baseline."""
+    r = ol.reference()
+    inp = ol.ref_inputs(n_iso, n_gp, gt, hb, lookups=lookups, hm=b"small" if n_iso == 68 else b"large", nthreads=NTHREADS)
+    sd = r.grid_init_do_not_profile(inp, 1)
+    k0 = r.run_event_based_simulation(inp, sd, 1)
+    k1 = r.run_event_based_simulation_optimization_1(inp, sd, 1)
+    p = ol.OracleProblem(n_iso, n_gp, gt, hb)
+    assert k1 == k0 == p.event(0, lookups, NTHREADS)
+    p.close()
+
+
 def test_event_partition_is_exact():
     p = ol.OracleProblem(68, 300, 0)
     whole = p.event(0, 10000, NTHREADS)

@@ -51,13 +51,22 @@ struct Problem {
     int    n_gp;
     int    hash_bins;
     int    mat_total;            // mat_first[12]
+    double mat_threshold[kNumMaterials];   // pick_mat's cumulative thresholds (summed in the reference's order)
 };
 
-__constant__ double c_mat_threshold[kNumMaterials];
-// Concentrations for the window kernel: one zero-padded row per material, read through the
-// uniform datapath (LDC) with no bounds logic -- padded steps simply multiply by 0.
-constexpr int kConcStride = 512;
-__constant__ double c_conc_pad[kNumMaterials * kConcStride];
+// Concentrations for the sweep / sorted / dense kernels: one zero-padded row per material, read
+// through the uniform datapath (LDC / LDCU on the kernel-parameter bank) with no bounds logic --
+// padded steps simply multiply by 0.  The table is a KERNEL PARAMETER (by value, 8 KB of the 32 KB
+// sm_100 allows): it belongs to the context that launches, so two live contexts with different
+// material tables cannot clobber each other (a __constant__ symbol is process-global -- round 1
+// kept it there).  Row m starts at first[m] (even: 16-byte aligned), holds num_nucs[m]
+// concentrations and at least kConcPad zeros.
+constexpr int kConcCap = 1024;
+constexpr int kConcPad = 8;
+struct ConcTable {
+    double v[kConcCap];
+    int    first[kNumMaterials];
+};
 
 // ---------------------------------------------------------------------------------------
 // LCG: x <- (a x + 1) mod 2^63
@@ -87,12 +96,12 @@ XS_DEV Affine lcg_jump(uint64_t n)
 XS_DEV uint64_t lcg_skip(uint64_t s, uint64_t n) { return apply(lcg_jump(n), s); }
 
 // First i with roll < thr[i] (thr[0] == 0 never matches), else 0 = fuel.
-XS_DEV int pick_material(double roll)
+XS_DEV int pick_material(const Problem &P, double roll)
 {
     int m = 0;
 #pragma unroll
     for (int i = kNumMaterials - 1; i >= 1; i--)
-        if (roll < c_mat_threshold[i]) m = i;     // descending scan keeps the FIRST match
+        if (roll < P.mat_threshold[i]) m = i;     // descending scan keeps the FIRST match
     return m;
 }
 
@@ -334,7 +343,8 @@ XS_DEV long hash_bin(const Problem &P, double e)
 {
     const double du = 1.0 / (double)P.hash_bins;
     long b = (long)(e / du);
-    return b > P.hash_bins - 1 ? P.hash_bins - 1 : b;   // E == 1.0 would read out of bounds
+    b = b > P.hash_bins - 1 ? P.hash_bins - 1 : b;      // E == 1.0 would read out of bounds
+    return b < 0 ? 0 : b;                               // (so would a negative energy; the sampler never draws one)
 }
 
 template <int GRID>

@@ -85,13 +85,14 @@ struct DeviceState {
     int *mat_first = nullptr, *mat_nuc = nullptr;
     double *mat_conc = nullptr;
     xs::Problem P{};
+    xs::ConcTable conc{};                  // zero-padded concentrations per material: a kernel PARAMETER, so it is this context's own
     size_t resident_bytes = 0;
     // per-run scratch
-    unsigned long long *accum = nullptr;   // device [2]
+    unsigned long long *accum = nullptr;   // device [3]: verification sum, lookups done, rejected host samples
     unsigned int *counters = nullptr;      // device [kNumCounters]
     unsigned int *histogram = nullptr;     // device [16]
     unsigned int *dense_counter = nullptr; // lane-per-lookup kernels: [0] next warp-group, [1] warps done (the kernel re-arms both)
-    unsigned long long *h_accum = nullptr; // pinned host [2]
+    unsigned long long *h_accum = nullptr; // pinned host [3]
     unsigned int *h_hist = nullptr;        // pinned host [16]
     int h_mat_first[XS_NUM_MATERIALS + 1] = {};
     long sample_capacity = 0;
@@ -174,7 +175,7 @@ EventKernel event_kernel(int grid, int gather)
     return table[grid][gather];
 }
 
-typedef void (*WindowKernel)(const xs::Problem, const xs::WindowArgs, const xs::BatchSink);
+typedef void (*WindowKernel)(const xs::Problem, const xs::WindowArgs, const xs::BatchSink, const xs::ConcTable);
 WindowKernel window_kernel(int grid)
 {
     using namespace xs;
@@ -357,17 +358,24 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         for (int j = i; j >= 1; j--) acc += frac[j];
         thr[i] = acc;
     }
-    CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_mat_threshold, thr, sizeof thr, 0, cudaMemcpyHostToDevice, d.stream));
-    if (sd->max_num_nucs + 16 > xs::kConcStride)
-        return set_error(XS_ERR_UNSUPP, "a material has %d nuclides, more than the %d this build supports", sd->max_num_nucs, xs::kConcStride - 16);
-    std::vector<double> conc_pad((size_t)XS_NUM_MATERIALS * xs::kConcStride, 0.0);
-    for (int m = 0; m < XS_NUM_MATERIALS; m++)
-        for (int j = 0; j < sd->num_nucs[m]; j++)
-            conc_pad[(size_t)m * xs::kConcStride + j] = sd->concs[(size_t)m * sd->max_num_nucs + j];
-    CUDA_TRY(cudaMemcpyToSymbolAsync(xs::c_conc_pad, conc_pad.data(), conc_pad.size() * sizeof(double), 0, cudaMemcpyHostToDevice, d.stream));
+    memcpy(P.mat_threshold, thr, sizeof thr);
+    // zero-padded concentration rows (kernel parameter, see xs::ConcTable)
+    {
+        int at = 0;
+        memset(&d.conc, 0, sizeof d.conc);
+        for (int m = 0; m < XS_NUM_MATERIALS; m++) {
+            d.conc.first[m] = at;
+            const int padded = (sd->num_nucs[m] + 7) / 8 * 8 + xs::kConcPad;
+            if (at + padded > xs::kConcCap)
+                return set_error(XS_ERR_UNSUPP, "the materials hold %d nuclide entries (padded), more than the %d this build supports",
+                                 at + padded, xs::kConcCap);
+            for (int j = 0; j < sd->num_nucs[m]; j++) d.conc.v[at + j] = sd->concs[(size_t)m * sd->max_num_nucs + j];
+            at += padded;
+        }
+    }
 
     // run scratch
-    CUDA_TRY(cudaMalloc(&d.accum, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d.accum, 3 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&d.counters, kNumCounters * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&d.histogram, kNumHist * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&d.dense_counter, 2 * sizeof(unsigned int)));
@@ -375,7 +383,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreateWithFlags(&d.ev_copy[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming));
-    CUDA_TRY(cudaMallocHost(&d.h_accum, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost(&d.h_accum, 3 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&d.h_hist, 16 * sizeof(unsigned int)));
 
     CUDA_TRY(cudaStreamSynchronize(d.stream));   // host vectors above go out of scope
@@ -510,7 +518,7 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
     if (rc != XS_OK) return rc;
     const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
     if (blocks > max_useful) blocks = (int)max_useful;
-    k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink);
+    k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, sink, d.conc);
     CUDA_TRY(cudaGetLastError());
     d.launches++;
     return XS_OK;
@@ -562,7 +570,7 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
         if (blocks > max_useful) blocks = (int)max_useful;
         xs::BatchSink launch_sink = sink;
         launch_sink.batch_counter = d.dense_counter;          // group hand-out; the kernel leaves it zeroed
-        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, launch_sink);
+        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, launch_sink, d.conc);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
     }
@@ -783,7 +791,7 @@ int enqueue_event_all(xs_gpu_ctx *ctx, int kernel_id, long first_id, long count)
         CUDA_TRY(cudaSetDevice(d.device));
         d.launches = 0;
         CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
     }
     const long max_pass = kernel_id == 0 ? std::max<long>(most, 1) : std::max<long>(ctx->max_pass, 1);
     bool more = true, first = true;
@@ -905,7 +913,7 @@ int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n
     CUDA_TRY(cudaSetDevice(d.device));
     d.launches = 0;
     CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
     CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
@@ -942,7 +950,7 @@ int finish_run(xs_gpu_ctx *ctx, xs_gpu_result *res, double host_t0)
     for (int g = 0; g < n; g++) {
         DeviceState &d = ctx->dev[g];
         CUDA_TRY(cudaSetDevice(d.device));
-        CUDA_TRY(cudaMemcpyAsync(d.h_accum, d.accum, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaMemcpyAsync(d.h_accum, d.accum, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
         CUDA_TRY(cudaEventRecord(d.ev[EV_DONE], d.stream));
     }
     memset(res, 0, sizeof *res);
@@ -1169,7 +1177,7 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         CUDA_TRY(cudaSetDevice(d.device));
         d.launches = 0;
         CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
         CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
         CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
         xs::BatchSink sink{};
@@ -1196,7 +1204,8 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                 xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
                                                                  d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
                                                                  d.histogram + 16 * c,
-                                                                 ctx->e2e_kernel == 6 && ctx->pack_samples ? d.samp_pack + c_lo : nullptr);
+                                                                 ctx->e2e_kernel == 6 && ctx->pack_samples ? d.samp_pack + c_lo : nullptr,
+                                                                 d.accum + 2);
                 CUDA_TRY(cudaGetLastError());
                 d.launches++;
                 if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
@@ -1208,6 +1217,12 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         } else {
             CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
             CUDA_TRY(cudaMemcpyAsync(d.samp_mat, h_mat + lo, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+            if (cnt > 0) {
+                const int vblocks = (int)std::min<long>((cnt + 255) / 256, (long)d.sm_count * 16);
+                xs::xs_validate_samples_kernel<<<vblocks, 256, 0, d.stream>>>(cnt, d.samp_e, d.samp_mat, d.accum + 2);
+                CUDA_TRY(cudaGetLastError());
+                d.launches++;
+            }
             CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
             CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
             sink.macro_out = h_macro_xs_out ? d.dump_macro : nullptr;
@@ -1223,6 +1238,11 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
     }
     int rc = finish_run(ctx, res, t0);
     if (rc != XS_OK) return rc;
+    unsigned long long rejected = 0;
+    for (int g = 0; g < ng; g++) rejected += ctx->dev[g].h_accum[2];
+    if (rejected)
+        return set_error(XS_ERR_ARG, "xs_gpu_lookup_samples: %llu sample(s) with a material outside [0, %d) or an energy outside [0, 1]",
+                         rejected, XS_NUM_MATERIALS);
     res->h2d_bytes = (unsigned long long)n * (sizeof(double) + sizeof(int));
     if (h_macro_xs_out) res->d2h_bytes += (unsigned long long)n * 5 * sizeof(double);
     return XS_OK;
@@ -1243,7 +1263,7 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
     CUDA_TRY(cudaMalloc(&d_macro, (size_t)n * 5 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&d_mat, (size_t)n * sizeof(int)));
     CUDA_TRY(cudaMalloc(&d_am, (size_t)n * sizeof(int)));
-    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 2 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     xs::BatchSource src{};
     src.first_id = first_id; src.count = n; src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;

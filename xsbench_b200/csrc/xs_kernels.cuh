@@ -318,7 +318,7 @@ xs_event_kernel(const Problem P, const BatchSource src, const BatchSink sink)
             } else {
                 uint64_t s = lcg_skip(kStartSeed, 2ULL * (uint64_t)(src.first_id + slot));
                 s = lcg_step(s); e_l = lcg_to_double(s);
-                s = lcg_step(s); mat_l = pick_material(lcg_to_double(s));
+                s = lcg_step(s); mat_l = pick_material(P, lcg_to_double(s));
             }
         }
         const bool want = have && mat_l >= src.mat_lo && mat_l <= src.mat_hi;
@@ -536,7 +536,7 @@ XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1]
 
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_SWEEP_BLOCKS)
-xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
+xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink, const ConcTable C)
 {
     __shared__ unsigned long long s_part[kWarpsPerBlock];
     __shared__ uint32_t s_rec[kWarpsPerBlock][kSweepSlots][kMaxWindow + 1];
@@ -612,7 +612,7 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 
         // ---- software-pipelined gather: no predication, padded steps multiply by 0 ----------
         const uint32_t *my_rec = s_rec[warp][slot];
-        const int ci = S.mat * kConcStride + S.j_begin;
+        const int ci = C.first[S.mat] + S.j_begin;
         Quarter A0[kSweepUnroll], A1[kSweepUnroll];
 #pragma unroll
         for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
@@ -624,14 +624,14 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A0[u], e0, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+                sweep_step(A0[u], e0, C.v[ci + j0 + u], f_src, acc_x, acc_y);
             e1 = order_after(e, acc_x);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
                 A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A1[u], e1, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+                sweep_step(A1[u], e1, C.v[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
             e0 = order_after(e, acc_x);
         }
         {   // last iteration: nothing left to prefetch
@@ -640,11 +640,11 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A0[u], e0, c_conc_pad[ci + j0 + u], f_src, acc_x, acc_y);
+                sweep_step(A0[u], e0, C.v[ci + j0 + u], f_src, acc_x, acc_y);
             e1 = order_after(e, acc_x);
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A1[u], e1, c_conc_pad[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+                sweep_step(A1[u], e1, C.v[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
         }
 
         if (!A.last_window) {
@@ -887,7 +887,7 @@ XS_DEV void finish_launch(const WindowArgs &A, const BatchSink &sink, unsigned i
 
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_SORTED_BLOCKS)
-xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
+xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink, const ConcTable C)
 {
     constexpr bool kStaged = GRID == kUnionized;
     __shared__ unsigned long long s_part[kWarpsPerBlock];
@@ -917,7 +917,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         // the records of all the others
         load_lane_samples<kPerLane>(A, S, first_in_seg, S.offset + S.count - 1, e, where32, on);
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
-        const int ci = S.mat * kConcStride;
+        const int ci = C.first[S.mat];
         double acc[kPerLane][5];
 #pragma unroll
         for (int w = 0; w < kPerLane; w++)
@@ -1022,7 +1022,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int step = j + h;
-                        const double conc = c_conc_pad[ci + c0 + step];
+                        const double conc = C.v[ci + c0 + step];
                         const uint32_t no_first = first_rec[step];
                         const uint32_t slot = ring + (uint32_t)((step % kRing) * kSlotBytes);
                         PairRecord r;
@@ -1050,7 +1050,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
                 };
                 // one step of all the lane's lookups; `r` holds the record of lookup 0 on entry
                 auto lane_step = [&](PairRecord &r, uint32_t no, int j) {
-                    const double conc = c_conc_pad[ci + c0 + j];
+                    const double conc = C.v[ci + c0 + j];
                     record_step(r, e[0], conc, acc[0]);
 #pragma unroll
                     for (int w = 1; w < kPerLane; w++) {
@@ -1136,7 +1136,7 @@ XS_DEV long long lds_s64(uint32_t smem_addr)
 
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_DENSE_BLOCKS)
-xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
+xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink, const ConcTable C)
 {
     __shared__ unsigned long long s_part[kWarpsPerBlock];
     extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][(first record, count) per step][nuclide ids]
@@ -1187,7 +1187,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
         const double e_min = __longlong_as_double(eb_min), e_max = __longlong_as_double(eb_max);
 
         const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
-        const int ci = S.mat * kConcStride;
+        const int ci = C.first[S.mat];
         double acc[kDensePerLane][5];
 #pragma unroll
         for (int w = 0; w < kDensePerLane; w++)
@@ -1290,7 +1290,7 @@ xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink)
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int step = j + h;
-                    const double conc = c_conc_pad[conc_base + step];
+                    const double conc = C.v[conc_base + step];
                     const uint32_t slot = ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes);
                     // which ring record each of the lane's lookups uses, and whether that is settled
                     uint32_t addr[kDensePerLane];
@@ -1428,7 +1428,7 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
         const Affine hop = lcg_jump(2ULL * (uint64_t)stride);
         for (; t < count; t += stride) {
             const uint64_t s1 = lcg_step(s), s2 = lcg_step(s1);
-            const int m = pick_material(lcg_to_double(s2));
+            const int m = pick_material(P, lcg_to_double(s2));
             const double e = lcg_to_double(s1);
             if (energy) energy[t] = e;
             if (mat) mat[t] = m;
@@ -1479,7 +1479,7 @@ xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long
         s = lcg_step(s);
         const double e = lcg_to_double(s);
         s = lcg_step(s);
-        const int m = pick_material(lcg_to_double(s));
+        const int m = pick_material(P, lcg_to_double(s));
         seeds[t] = s;
         energy[t] = e;
         mat[t] = m;
@@ -1491,23 +1491,39 @@ xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long
         atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
 }
 
-// Same bookkeeping for samples that already exist (host-provided): where + histogram.
+// Same bookkeeping for samples that already exist (host-provided): where + histogram.  The samples
+// come from outside the library, so they are validated here: a material outside [0, 12) or an energy
+// outside [0, 1] (NaN included) would index shared-memory histograms, material tables and the
+// hash / unionized grids out of bounds further down.  Such a sample is counted in *bad (the call
+// then fails with XS_ERR_ARG) and replaced in place by a harmless one, so nothing downstream can fault.
+XS_DEV bool sanitize_sample(double &e, int &m)
+{
+    const bool ok = (unsigned)m < (unsigned)kNumMaterials && e >= 0.0 && e <= 1.0;
+    if (!ok) { e = 0.5; m = 0; }
+    return ok;
+}
+
 __global__ void __launch_bounds__(256)
-xs_locate_kernel(const Problem P, int grid_type, long count, const double *energy, const int *mat,
-                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, double2 *pack)
+xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int *mat,
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, double2 *pack, unsigned long long *bad)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
-        const double e = energy[t];
-        const int m = mat[t];
+        double e = energy[t];
+        int m = mat[t];
+        if (!sanitize_sample(e, m)) {
+            atomicAdd(bad, 1ULL);
+            energy[t] = e;
+            mat[t] = m;
+        }
         const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
         where[t] = w;
         if (pack) pack[t] = make_double2(e, __longlong_as_double((long long)w));
         if (key) {    // same layout as the sampler's key: material, then 28 bits monotone in the energy
-            const double scaled = fmin(fmax(e, 0.0) * 268435456.0, 268435455.0);
+            const double scaled = fmin(e * 268435456.0, 268435455.0);
             key[t] = ((uint32_t)m << 28) | (uint32_t)scaled;
         }
         atomicAdd(&s_hist[m], 1u);
@@ -1515,6 +1531,22 @@ xs_locate_kernel(const Problem P, int grid_type, long count, const double *energ
     __syncthreads();
     if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
         atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
+}
+
+// Validation only (the in-order kernel reads host samples directly: XSB200_SWEEP=0).
+__global__ void __launch_bounds__(256)
+xs_validate_samples_kernel(long count, double *energy, int *mat, unsigned long long *bad)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        double e = energy[t];
+        int m = mat[t];
+        if (!sanitize_sample(e, m)) {
+            atomicAdd(bad, 1ULL);
+            energy[t] = e;
+            mat[t] = m;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1633,7 +1665,7 @@ xs_history_kernel(const Problem P, long first_particle, long n_particles, int lo
         // all lanes carry the same state (warp-uniform control flow)
         uint64_t s = lcg_skip(kStartSeed, p * (uint64_t)lookups * 10ULL);
         s = lcg_step(s); double e = lcg_to_double(s);
-        s = lcg_step(s); int mat = pick_material(lcg_to_double(s));
+        s = lcg_step(s); int mat = pick_material(P, lcg_to_double(s));
         for (int i = 0; i < lookups; i++) {
             const long where = locate<GRID>(P, e);
             const int first = T.first[mat], n = T.first[mat + 1] - first;
@@ -1655,7 +1687,7 @@ xs_history_kernel(const Problem P, long first_particle, long n_particles, int lo
             my_count += 1;
             for (int k = 0; k < fwd; k++) s = lcg_step(s);
             s = lcg_step(s); e = lcg_to_double(s);
-            s = lcg_step(s); mat = pick_material(lcg_to_double(s));
+            s = lcg_step(s); mat = pick_material(P, lcg_to_double(s));
         }
     }
     if (lane != 0) { my_sum = 0; my_count = 0; }

@@ -52,6 +52,29 @@ int main(int argc, char *argv[])
     xs_gpu_get_info(ctx, &info);
     printf("GPU Intialization complete. Allocated %.0lf MB of data on each GPU.\n",
            info.resident_bytes / 1024.0 / 1024.0);
+    if (in.binary_mode == XS_BINARY_WRITE && opt.device_init) {
+        /* the problem exists on the device only: fetch the three big arrays, then write the file */
+        const long n_points = in.n_isotopes * in.n_gridpoints;
+        SD.length_nuclide_grid = (int)n_points;
+        SD.nuclide_grid = malloc((size_t)n_points * sizeof(NuclideGridPoint));
+        SD.length_unionized_energy_array = in.grid_type == XS_UNIONIZED ? (int)n_points : 0;
+        SD.length_index_grid = in.grid_type == XS_UNIONIZED ? n_points * in.n_isotopes
+                             : in.grid_type == XS_HASH ? (long)in.hash_bins * in.n_isotopes : 0;
+        if (SD.length_unionized_energy_array)
+            SD.unionized_energy_array = malloc((size_t)n_points * sizeof(double));
+        if (SD.length_index_grid)
+            SD.index_grid = malloc((size_t)SD.length_index_grid * sizeof(int));
+        int rc = SD.nuclide_grid ? xs_gpu_read_array(ctx, XS_ARRAY_NUCLIDE_GRID, 0, n_points * 48, SD.nuclide_grid) : XS_ERR_ARG;
+        if (rc == XS_OK && SD.length_unionized_energy_array)
+            rc = SD.unionized_energy_array ? xs_gpu_read_array(ctx, XS_ARRAY_UNIONIZED_ENERGY, 0, n_points * 8, SD.unionized_energy_array) : XS_ERR_ARG;
+        if (rc == XS_OK && SD.length_index_grid)
+            rc = SD.index_grid ? xs_gpu_read_array(ctx, XS_ARRAY_INDEX_GRID, 0, SD.length_index_grid * 4, SD.index_grid) : XS_ERR_ARG;
+        if (rc != XS_OK) {
+            fprintf(stderr, "-b write with --device-init: cannot fetch the generated problem: %s\n", xs_gpu_last_error());
+            return 2;
+        }
+        binary_write(in, SD);
+    }
     xs_free_simulation_data(&SD);     /* the device copy is self-contained */
 
     printf("\n");
