@@ -131,6 +131,8 @@ typedef struct {
     long   n_isotopes, n_gridpoints;
     int    grid_type, hash_bins, max_num_nucs;
     long   n_ueg;                        /* rows of the unionized grid (0 otherwise)         */
+    int    fp64_ops_per_pair;            /* FP64 operations per (lookup, nuclide) of the -k 6 dense kernel: 24 = the reference's
+                                            roundings (default), 12 = fused (XSB200_ARITH=fused)                              */
 } xs_gpu_info;
 
 /*

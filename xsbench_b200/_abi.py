@@ -74,7 +74,7 @@ class GpuInfo(C.Structure):
     _fields_ = [("device", C.c_int), ("sm_count", C.c_int), ("l2_bytes", C.c_long),
                 ("resident_bytes", C.c_long), ("n_isotopes", C.c_long), ("n_gridpoints", C.c_long),
                 ("grid_type", C.c_int), ("hash_bins", C.c_int), ("max_num_nucs", C.c_int),
-                ("n_ueg", C.c_long)]
+                ("n_ueg", C.c_long), ("fp64_ops_per_pair", C.c_int)]
 
 
 class DriverOpts(C.Structure):

@@ -20,6 +20,7 @@
 
 #include "xs_gpu.h"
 #include "xs_kernels.cuh"
+#include "xs_dense.cuh"
 #include "xs_sort.cuh"
 #include "xs_generate.cuh"
 
@@ -147,6 +148,8 @@ struct xs_gpu_ctx {
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
+    int exact_arith = 1;                   // xs_dense_kernel: 1 = the reference's roundings (24 FP64 operations per (lookup, nuclide), macro_xs
+                                           // bit-identical), 0 = fused (12 operations, within 1e-12, integers guarded): XSB200_ARITH=fused
     int dense_min = 64;                    // -k 6: materials with >= this many lookups per grid interval go to xs_dense_kernel (0 = never)
     int key_lo_bit = 8;                    // -k 6 sorts key bits [key_lo_bit, 32): material + 20 energy bits
     int num_nucs[XS_NUM_MATERIALS] = {};
@@ -194,12 +197,13 @@ HistoryKernel history_kernel(int grid, int gather)
     return table[grid][gather];
 }
 
-int persistent_grid(const xs_gpu_ctx *ctx, const DeviceState &d, const void *kernel, int *blocks, long smem = -1)
+int persistent_grid(const xs_gpu_ctx *ctx, const DeviceState &d, const void *kernel, int *blocks, long smem = -1,
+                    int threads = xs::kBlockThreads)
 {
     const size_t dyn_smem = smem < 0 ? ctx->smem_bytes : (size_t)smem;
     int per_sm = ctx->blocks_per_sm;
     if (per_sm <= 0) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, xs::kBlockThreads, dyn_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
         if (per_sm < 1) per_sm = 1;
     }
     *blocks = per_sm * d.sm_count;
@@ -529,9 +533,10 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
 // interval or the next) go to xs_dense_kernel, the others to xs_sorted_kernel -- two launches.
 int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::BatchSink sink)
 {
-    static const WindowKernel table[2][3] = {
+    static const WindowKernel table[3][3] = {
         { xs::xs_sorted_kernel<xs::kUnionized>, xs::xs_sorted_kernel<xs::kNuclide>, xs::xs_sorted_kernel<xs::kHash> },
-        { xs::xs_dense_kernel<xs::kUnionized>, xs::xs_dense_kernel<xs::kNuclide>, xs::xs_dense_kernel<xs::kHash> } };
+        { xs::xs_dense_kernel<xs::kUnionized, true>, xs::xs_dense_kernel<xs::kNuclide, true>, xs::xs_dense_kernel<xs::kHash, true> },
+        { xs::xs_dense_kernel<xs::kUnionized, false>, xs::xs_dense_kernel<xs::kNuclide, false>, xs::xs_dense_kernel<xs::kHash, false> } };
     for (int dense = 1; dense >= 0; dense--) {
         xs::WindowArgs a{};
         long groups = 0;
@@ -555,22 +560,23 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
         a.indirect = b.indirect;
         a.pack = b.pack;
         a.first_window = a.last_window = 1;
-        WindowKernel k = table[dense][ctx->grid_type];
+        WindowKernel k = table[dense ? (ctx->exact_arith ? 1 : 2) : 0][ctx->grid_type];
         int blocks = 0;
         size_t staged = 0;
+        const int threads = dense ? xs::kDenseThreads : xs::kBlockThreads, warps = threads / 32;
         if (dense)
-            staged = (size_t)xs::kWarpsPerBlock * (xs::kDenseRingBytes + xs::kDenseFirstWords * sizeof(uint32_t));
+            staged = (size_t)warps * (xs::kDenseRingBytes + xs::kDenseFirstWords * sizeof(uint32_t));
         else if (ctx->grid_type == XS_UNIONIZED)
             staged = (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes);
         const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
         CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
+        int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem, threads);
         if (rc != XS_OK) return rc;
-        const long max_useful = (groups + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+        const long max_useful = (groups + warps - 1) / warps;
         if (blocks > max_useful) blocks = (int)max_useful;
         xs::BatchSink launch_sink = sink;
         launch_sink.batch_counter = d.dense_counter;          // group hand-out; the kernel leaves it zeroed
-        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, a, launch_sink, d.conc);
+        k<<<blocks, threads, smem, d.stream>>>(d.P, a, launch_sink, d.conc);
         CUDA_TRY(cudaGetLastError());
         d.launches++;
     }
@@ -1040,6 +1046,10 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->pack_samples = env_int("XSB200_PACK_SAMPLES", 1);
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
+    {
+        const char *arith = getenv("XSB200_ARITH");
+        ctx->exact_arith = !(arith && (!strcmp(arith, "fused") || !strcmp(arith, "12")));
+    }
     ctx->key_lo_bit = std::min(28, std::max(0, env_int("XSB200_KEY_LO_BIT", 8)));
     for (int m = 0; m < XS_NUM_MATERIALS; m++) ctx->num_nucs[m] = sd->num_nucs[m];
     ctx->dev.resize(n_gpus);
@@ -1353,6 +1363,7 @@ int xs_gpu_get_info(const xs_gpu_ctx *ctx, xs_gpu_info *info)
     info->hash_bins = ctx->hash_bins;
     info->max_num_nucs = ctx->max_num_nucs;
     info->n_ueg = ctx->n_ueg;
+    info->fp64_ops_per_pair = ctx->exact_arith ? 24 : 12;
     return XS_OK;
 }
 

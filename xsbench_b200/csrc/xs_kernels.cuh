@@ -1081,283 +1081,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
     finish_launch(A, sink, my_sum, s_part);
 }
 
-// ---------------------------------------------------------------------------------------
-// xs_dense_kernel -- the sorted kernel for DENSE segments (many lookups per grid interval:
-// large/fuel has 209).  The 96 energy-sorted lookups of a warp-group (3 per lane) then fall, per
-// nuclide, into ONE grid interval (63 % of the steps of large/fuel) or a few consecutive ones.  So only
-// the group's lowest and highest energy are resolved (lane l resolves nuclide c0 + l: two
-// index-row segments per group and chunk instead of 96, or two bucket-table searches per nuclide
-// instead of 96 in hash / nuclide mode), which gives, per nuclide, the first record k_min and
-// the number of records n = k_max - k_min + 1 the group can touch (the search is monotone in
-// the energy).  n records (at most kDenseSpan) go through the shared-memory ring.
-//   n == 1: every lookup of the group uses that record -- no per-lookup work at all;
-//   n >= 2: a lookup picks its record by comparing its energy with the interval bounds stored in
-//           the ring records; a lookup beyond the ring, or exactly ON a bound (where the
-//           reference's hash-grid procedure has its own ideas), resolves its own interval with
-//           the reference's procedure (nuclide_low).
-// Results therefore never depend on how well the batch is sorted: min / max are taken over the
-// group, not assumed from positions.  The next chunk is resolved (and its records requested
-// into L2) before the current one is gathered: no staging phase, no transposition, 1/48 of the
-// index-grid traffic of xs_sorted_kernel.
-// ---------------------------------------------------------------------------------------
-#ifndef XS_DENSE_BLOCKS
-#define XS_DENSE_BLOCKS 2
-#endif
-#ifndef XS_DENSE_RING
-#define XS_DENSE_RING 8
-#endif
-#ifndef XS_DENSE_SPAN
-#define XS_DENSE_SPAN 4
-#endif
-#ifndef XS_DENSE_PER_LANE
-#define XS_DENSE_PER_LANE 3          // measured (lookup phase of -k 6, large): 2 -> 2.35 ms, 3 -> 2.21, 4 -> 2.26
-#endif
-constexpr int kDensePerLane = XS_DENSE_PER_LANE;       // consecutive lookups per lane
-constexpr int kDenseGroup = 32 * kDensePerLane;        // lookups per warp-group
-constexpr int kDenseRing = XS_DENSE_RING;              // steps of records in flight per warp (a power of two)
-constexpr int kDenseSpan = XS_DENSE_SPAN;              // records per ring slot (2..4)
-constexpr int kDenseSlotBytes = kDenseSpan * 128;
-constexpr int kDenseRingBytes = kDenseRing * kDenseSlotBytes;
-constexpr int kDenseFirstWords = 2 * 32 * 2;           // per warp: (first record, record count) per step, double-buffered by chunk
-static_assert((kDenseRing & (kDenseRing - 1)) == 0 && kDenseSpan >= 2 && kDenseSpan <= 4, "dense kernel ring geometry");
-
-XS_DEV uint2 lds_v2_u32(uint32_t smem_addr)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_addr));
-    return v;
-}
-XS_DEV long long lds_s64(uint32_t smem_addr)
-{
-    long long v;
-    asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(smem_addr));
-    return v;
-}
-
-template <int GRID>
-__global__ void __launch_bounds__(kBlockThreads, XS_DENSE_BLOCKS)
-xs_dense_kernel(const Problem P, const WindowArgs A, const BatchSink sink, const ConcTable C)
-{
-    __shared__ unsigned long long s_part[kWarpsPerBlock];
-    extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][(first record, count) per step][nuclide ids]
-    uint32_t *s_first = s_dyn + kWarpsPerBlock * kDenseRingBytes / 4;
-    int *s_nuc = (int *)(s_first + kWarpsPerBlock * kDenseFirstWords);
-    for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int my_sum = 0;
-    uint2 *warp_first = (uint2 *)(s_first + warp * kDenseFirstWords);
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + warp * kDenseRingBytes;
-    const uint32_t first_base = (uint32_t)__cvta_generic_to_shared(warp_first);
-
-    int g = warp_next_group(sink, lane);
-    while (g < A.n_groups) {
-        const int g_next = warp_next_group(sink, lane);      // (known early: its samples are requested below)
-        const int sg = segment_of_group(A, g);
-        const WindowSegment &S = A.seg[sg];
-        const int group_first = (g - S.group_begin) * kDenseGroup;
-        const int first_in_seg = group_first + lane * kDensePerLane;
-        const long t0 = S.offset + first_in_seg;
-        double e[kDensePerLane];
-        uint32_t where32[kDensePerLane];
-        bool on[kDensePerLane];
-        // idle slots repeat the group's first lookup: they do not widen the group's energy range
-        load_lane_samples<kDensePerLane>(A, S, first_in_seg, S.offset + group_first, e, where32, on);
-        // The group's energy range.  Energies are non-negative doubles: their bit patterns order
-        // like the values (and 64-bit integer compares run on the ALU pipe instead of queueing
-        // behind the FP64 work).  The UEG row / hash bin is monotone in the energy, so the
-        // extreme rows belong to the extreme energies.
-        long long eb_min = __double_as_longlong(e[0]), eb_max = eb_min;
-        uint32_t where_min = where32[0], where_max = where32[0];
-#pragma unroll
-        for (int w = 1; w < kDensePerLane; w++) {
-            eb_min = min(eb_min, __double_as_longlong(e[w]));
-            eb_max = max(eb_max, __double_as_longlong(e[w]));
-            where_min = min(where_min, where32[w]);
-            where_max = max(where_max, where32[w]);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            eb_min = min(eb_min, __shfl_xor_sync(kFullMask, eb_min, off));
-            eb_max = max(eb_max, __shfl_xor_sync(kFullMask, eb_max, off));
-        }
-        where_min = __reduce_min_sync(kFullMask, where_min);
-        where_max = __reduce_max_sync(kFullMask, where_max);
-        const double e_min = __longlong_as_double(eb_min), e_max = __longlong_as_double(eb_max);
-
-        const int n_nuc = S.j_end;                            // whole material (j_begin = 0)
-        const int ci = C.first[S.mat];
-        double acc[kDensePerLane][5];
-#pragma unroll
-        for (int w = 0; w < kDensePerLane; w++)
-#pragma unroll
-            for (int k = 0; k < 5; k++) acc[w][k] = 0.0;
-
-        // lane l: the records the group can touch in nuclide c + l (columns past the end repeat
-        // the material's last nuclide: valid records, only ever used with concentration 0)
-        uint32_t multi_next = 0, two_next = 0;
-        auto resolve = [&](int c, int buf) {
-            const int nuc_l = s_nuc[S.first + min(c + lane, n_nuc - 1)];
-            const int k_lo = nuclide_low<GRID, false>(P, e_min, (long)where_min, nuc_l);
-            const int k_hi = nuclide_low<GRID, false>(P, e_max, (long)where_max, nuc_l);
-            int n = k_hi - k_lo + 1;
-            // The hash-grid procedure maps an energy that EQUALS the grid point at the edge of its
-            // bin's bracket to the nuclide's first / last interval (cuda/Simulation.cu:150-156).
-            // Should both ends of the group be such points, the lookups in between are not: let
-            // every lookup of this step resolve itself (n = 0).
-            if (GRID == kHash && k_lo == k_hi && (k_lo == 0 || k_lo == P.n_gp - 2)) n = 0;
-            n = min(max(n, 0), 0xffff);
-            const uint32_t no = (uint32_t)nuc_l * (uint32_t)P.n_gp + (uint32_t)k_lo;
-            // (count in the low half, the number of 16-byte pieces the ring copy moves in the high half)
-            const uint32_t pieces = 8u * (uint32_t)min(max(n, 1), kDenseSpan);
-            warp_first[buf * 32 + lane] = make_uint2(no, (uint32_t)n | (pieces << 16));
-            multi_next = __ballot_sync(kFullMask, n != 1);  // bit l: step l of that chunk needs the per-lookup selection
-            two_next = __ballot_sync(kFullMask, n == 2);
-            // a record is used by ~one block only, so its first touch comes from DRAM: start now
-            prefetch_l2(P.pairs + 8 * (size_t)no);
-#pragma unroll
-            for (int i = 1; i < kDenseSpan; i++)
-                if (i < n) prefetch_l2(P.pairs + 8 * ((size_t)no + i));
-        };
-        // The warp's next group: fetch its sample ids now, request the samples behind them after
-        // the first chunk (two dependent random reads otherwise wait in front of every group).
-        uint32_t next_id[kDensePerLane];
-        bool next_any = false;
-        if (A.indirect && A.pack) {
-            const int g2 = g_next;
-            if (g2 < A.n_groups) {
-                const WindowSegment &S2 = A.seg[segment_of_group(A, g2, sg)];
-                const int first2 = (g2 - S2.group_begin) * kDenseGroup + lane * kDensePerLane;
-                next_any = true;
-#pragma unroll
-                for (int w = 0; w < kDensePerLane; w++)
-                    next_id[w] = A.sample_id[S2.offset + min(first2 + w, S2.count - 1)];
-            }
-        }
-        __syncwarp();
-        resolve(0, 0);
-        int buf = 0;
-        for (int c0 = 0; c0 < n_nuc; c0 += 32, buf ^= 1) {
-            if (c0 == 32 || (c0 == 0 && n_nuc <= 32)) {
-                if (next_any) {
-#pragma unroll
-                    for (int w = 0; w < kDensePerLane; w++) prefetch_l2(A.pack + next_id[w]);
-                }
-            }
-            const uint32_t multi = multi_next, two = two_next;   // known a chunk ahead, in registers: no load in front of the branches
-            const int jn = min(32, n_nuc - c0);
-            const int n_steps = (jn + 1) & ~1;               // an odd tail is padded: concentration 0
-            const int *nucs = s_nuc + S.first + c0;
-            __syncwarp();
-            if (GRID == kUnionized && c0 + 64 < n_nuc) {      // the index-row segments of the chunk after the next
-                const uint32_t row_w = (lane & 1) ? where_max : where_min;
-                const int *row = P.index_grid + (size_t)row_w * (uint32_t)P.n_iso;
-                if (lane < 2)        prefetch_l2(row + nucs[64]);
-                else if (lane >= 30) prefetch_l2(row + nucs[min(95, n_nuc - c0 - 1)]);
-            }
-            if (c0 + 32 < n_nuc) resolve(c0 + 32, buf ^ 1);
-
-            const uint32_t first_addr = first_base + (uint32_t)(buf * 32 * 8);   // shared address of this chunk's (first, count) pairs
-            // steps s, s+1 with their (first record, count) pairs: 8 lanes x 16 B per record
-            auto issue = [&](int s, uint2 d0, uint2 d1) {
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int step = s + q;
-                    const uint2 fc = q ? d1 : d0;
-                    if (step < n_steps && (uint32_t)lane < (fc.y >> 16))
-                        cp_async_16(ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes + lane * 16),
-                                    P.pairs + 8 * (size_t)fc.x + lane);
-                }
-                cp_async_commit();
-            };
-            auto resolve_own = [&](PairRecord &r, double e_w, uint32_t where_w, int step) {
-                const int nuc = nucs[min(step, jn - 1)];
-                const uint32_t no = (uint32_t)nuc * (uint32_t)P.n_gp
-                                    + (uint32_t)nuclide_low<GRID, false>(P, e_w, (long)where_w, nuc);
-                r = ldg_record(P.pairs + 8 * (size_t)no);
-            };
-#pragma unroll
-            for (int s = 0; s < kDenseRing; s += 2)
-                issue(s, lds_v2_u32(first_addr + s * 8), lds_v2_u32(first_addr + (s + 1) * 8));
-            // the pairs of the steps issued at the end of an iteration are fetched one iteration
-            // ahead (no load in front of the copy instructions)
-            uint2 d0 = lds_v2_u32(first_addr + (kDenseRing & 31) * 8), d1 = lds_v2_u32(first_addr + ((kDenseRing + 1) & 31) * 8);
-            const int conc_base = ci + c0;
-            for (int j = 0; j < n_steps; j += 2) {
-                cp_async_wait_group<kDenseRing / 2 - 1>();
-                __syncwarp();
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int step = j + h;
-                    const double conc = C.v[conc_base + step];
-                    const uint32_t slot = ring + (uint32_t)((step & (kDenseRing - 1)) * kDenseSlotBytes);
-                    // which ring record each of the lane's lookups uses, and whether that is settled
-                    uint32_t addr[kDensePerLane];
-                    bool ok[kDensePerLane];
-#pragma unroll
-                    for (int w = 0; w < kDensePerLane; w++) { addr[w] = slot; ok[w] = true; }
-                    if ((multi >> step) & 1u) {              // warp-uniform: more (or fewer) than one record
-                        if ((two >> step) & 1u) {
-                            // two records: one bound between them.  Nothing lies beyond the second
-                            // (the search is monotone); ON the bound the reference decides.
-                            const long long hi0 = lds_s64(slot + 96);
-#pragma unroll
-                            for (int w = 0; w < kDensePerLane; w++) {
-                                const long long eb = __double_as_longlong(e[w]);
-                                addr[w] = slot + (eb > hi0 ? 128u : 0u);
-                                ok[w] = eb != hi0;
-                            }
-                        } else {
-                            // record i covers (hi[i-1], hi[i]); a bound past the group's n records is
-                            // stale, but it is only looked at by a lookup already beyond them.  (The
-                            // last record's own bound matters when the group spans more than the ring.)
-                            long long hi[kDenseSpan];
-#pragma unroll
-                            for (int i = 0; i < kDenseSpan; i++) hi[i] = lds_s64(slot + i * 128 + 96);
-                            const uint32_t n_ring = min(lds_v2_u32(first_addr + step * 8).y & 0xffffu, (uint32_t)kDenseSpan);
-#pragma unroll
-                            for (int w = 0; w < kDensePerLane; w++) {
-                                const long long eb = __double_as_longlong(e[w]);
-                                uint32_t which = 0;
-                                bool beyond = true, on_bound = false;
-#pragma unroll
-                                for (int i = 0; i < kDenseSpan; i++) {
-                                    beyond = beyond & (eb > hi[i]);
-                                    which += beyond ? 1u : 0u;
-                                    on_bound = on_bound | (eb == hi[i]);
-                                }
-                                ok[w] = (which < n_ring) & !on_bound;
-                                addr[w] = slot + min(which, (uint32_t)(kDenseSpan - 1)) * 128;
-                            }
-                        }
-                    }
-                    PairRecord r = lds_record(addr[0]);
-                    if (!ok[0]) resolve_own(r, e[0], where32[0], step);
-                    record_step(r, e[0], conc, acc[0]);
-#pragma unroll
-                    for (int w = 1; w < kDensePerLane; w++) {
-                        if (addr[w] != addr[w - 1] || !ok[w] || !ok[w - 1]) {
-                            r = lds_record(addr[w]);
-                            if (!ok[w]) resolve_own(r, e[w], where32[w], step);
-                        }
-                        record_step(r, e[w], conc, acc[w]);
-                    }
-                }
-                __syncwarp();                                // everyone is done with these two slots
-                issue(j + kDenseRing, d0, d1);
-                d0 = lds_v2_u32(first_addr + ((j + 2 + kDenseRing) & 31) * 8);
-                d1 = lds_v2_u32(first_addr + ((j + 3 + kDenseRing) & 31) * 8);
-            }
-            cp_async_wait_group<0>();
-        }
-
-        finish_lane_lookups<kDensePerLane>(A, sink, t0, on, acc, my_sum);
-        g = g_next;
-    }
-    warp_groups_done(sink, lane);
-    finish_launch(A, sink, my_sum, s_part);
-}
+// (xs_dense_kernel, the kernel for dense segments, lives in xs_dense.cuh)
 
 // Per-nuclide bucket tables for nuclide-grid mode (init only): bucket[i][b] = number of grid
 // points of nuclide i whose energy maps to a bucket < b (same monotone map as the query).
