@@ -203,6 +203,8 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
     extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][(first record, count) per step][nuclide ids]
     uint32_t *s_first = s_dyn + kDenseWarps * kDenseRingBytes / 4;
     int *s_nuc = (int *)(s_first + kDenseWarps * kDenseFirstWords);
+    __shared__ SegTable T;
+    load_seg_table(A, T);
     for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
     __syncthreads();
 
@@ -221,10 +223,10 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
     const uint32_t desc_lane = opaque(first_base + (uint32_t)(q_l * 8));
 
     int g = warp_next_group(sink, lane);
-    while (g < A.n_groups) {
+    while (g < T.n_groups) {
         const int g_next = warp_next_group(sink, lane);      // (known early: its samples are requested below)
-        const int sg = segment_of_group(A, g);
-        const WindowSegment &S = A.seg[sg];
+        const int sg = segment_of_group(T, g);
+        const WindowSegment &S = T.seg[sg];
         const int group_first = (g - S.group_begin) * kDenseGroup;
         const int first_in_seg = group_first + lane * PL;
         const long t0 = S.offset + first_in_seg;
@@ -308,8 +310,8 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
         uint32_t next_id[PL];
         bool next_any = false;
         if (A.indirect && A.pack) {
-            if (g_next < A.n_groups) {
-                const WindowSegment &S2 = A.seg[segment_of_group(A, g_next, sg)];
+            if (g_next < T.n_groups) {
+                const WindowSegment &S2 = T.seg[segment_of_group(T, g_next, sg)];
                 const int first2 = (g_next - S2.group_begin) * kDenseGroup + lane * PL;
                 next_any = true;
 #pragma unroll
@@ -448,7 +450,7 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
         if (bs) atomicAdd(sink.accum, bs);
         if (blockIdx.x == 0) {
             unsigned long long done = 0;
-            for (int i = 0; i < A.n_seg; i++) done += (unsigned long long)A.seg[i].count;
+            for (int i = 0; i < T.n_seg; i++) done += (unsigned long long)T.seg[i].count;
             atomicAdd(sink.accum + 1, done);
         }
     }

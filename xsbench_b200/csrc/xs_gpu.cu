@@ -93,6 +93,7 @@ struct DeviceState {
     unsigned int *counters = nullptr;      // device [kNumCounters]
     unsigned int *histogram = nullptr;     // device [16]
     unsigned int *dense_counter = nullptr; // lane-per-lookup kernels: [0] next warp-group, [1] warps done (the kernel re-arms both)
+    xs::SegTable *seg_tables = nullptr;    // [kMaxChunks][2]: device-built segment tables (sparse, dense) of the host-sample pipeline
     unsigned long long *h_accum = nullptr; // pinned host [3]
     unsigned int *h_hist = nullptr;        // pinned host [16]
     int h_mat_first[XS_NUM_MATERIALS + 1] = {};
@@ -148,6 +149,8 @@ struct xs_gpu_ctx {
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
+    int device_segments = 1;               // -k 6 / host-sample pipeline: segment tables built on the device, no histogram read-back
+    int e2e_split[kMaxChunks] = {};        // XSB200_E2E_SPLIT: chunk sizes of a host-sample call, in percent (0 = built-in schedule)
     int exact_arith = 1;                   // xs_dense_kernel: 1 = the reference's roundings (24 FP64 operations per (lookup, nuclide), macro_xs
                                            // bit-identical), 0 = fused (12 operations, within 1e-12, integers guarded): XSB200_ARITH=fused
     int dense_min = 64;                    // -k 6: materials with >= this many lookups per grid interval go to xs_dense_kernel (0 = never)
@@ -384,6 +387,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     CUDA_TRY(cudaMalloc(&d.histogram, kNumHist * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&d.dense_counter, 2 * sizeof(unsigned int)));
     CUDA_TRY(cudaMemsetAsync(d.dense_counter, 0, 2 * sizeof(unsigned int), d.stream));
+    CUDA_TRY(cudaMalloc(&d.seg_tables, (size_t)kMaxChunks * 2 * sizeof(xs::SegTable)));
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreateWithFlags(&d.ev_copy[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming));
@@ -496,6 +500,8 @@ struct GroupedBatch {
     double2 *partial;
     long offset[XS_NUM_MATERIALS]; // first slot of each material (host copy of the histogram prefix)
     long count[XS_NUM_MATERIALS];  // lookups per material
+    const unsigned int *hist;      // device histogram of this batch (device-built segment tables)
+    long total;                    // lookups in the batch
 };
 
 // One launch of the window kernel over `a.n_seg` segments.
@@ -531,28 +537,43 @@ int launch_window(xs_gpu_ctx *ctx, DeviceState &d, xs::WindowArgs &a, const Grou
 // Lane-per-lookup sweep over a batch sorted by (material, energy): the materials with many lookups
 // per grid interval (>= ctx->dense_min: a warp-group's 96 lookups then fall into the first lookup's
 // interval or the next) go to xs_dense_kernel, the others to xs_sorted_kernel -- two launches.
-int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::BatchSink sink)
+int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::BatchSink sink, xs::SegTable *dev_tables = nullptr)
 {
     static const WindowKernel table[3][3] = {
         { xs::xs_sorted_kernel<xs::kUnionized>, xs::xs_sorted_kernel<xs::kNuclide>, xs::xs_sorted_kernel<xs::kHash> },
         { xs::xs_dense_kernel<xs::kUnionized, true>, xs::xs_dense_kernel<xs::kNuclide, true>, xs::xs_dense_kernel<xs::kHash, true> },
         { xs::xs_dense_kernel<xs::kUnionized, false>, xs::xs_dense_kernel<xs::kNuclide, false>, xs::xs_dense_kernel<xs::kHash, false> } };
+    if (dev_tables) {
+        // the segments of both launches from the histogram, on the device: the host does not wait for it
+        xs::MatShape shape;
+        for (int m = 0; m <= XS_NUM_MATERIALS; m++) shape.first[m] = d.h_mat_first[m];
+        for (int m = 0; m < XS_NUM_MATERIALS; m++) shape.n_nuc[m] = ctx->num_nucs[m];
+        xs::xs_build_segments_kernel<<<1, 32, 0, d.stream>>>(b.hist, shape, ctx->dense_min > 0 ? (long)ctx->dense_min * d.P.n_gp : 0L,
+                                                             xs::kDenseGroup, xs::kSortedGroup, dev_tables + 1, dev_tables + 0);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
+    }
     for (int dense = 1; dense >= 0; dense--) {
         xs::WindowArgs a{};
         long groups = 0;
-        for (int m = 0; m < XS_NUM_MATERIALS; m++) {
-            if (b.count[m] <= 0) continue;
-            const bool is_dense = ctx->dense_min > 0 && b.count[m] >= (long)ctx->dense_min * d.P.n_gp;
-            if (is_dense != (dense == 1)) continue;
-            xs::WindowSegment &sgm = a.seg[a.n_seg++];
-            sgm.mat = m; sgm.first = d.h_mat_first[m]; sgm.j_begin = 0; sgm.j_end = ctx->num_nucs[m];
-            sgm.offset = b.offset[m];
-            sgm.count = (int)b.count[m];
-            sgm.group_begin = (int)groups;
-            const int group = dense ? xs::kDenseGroup : xs::kSortedGroup;
-            groups += (b.count[m] + group - 1) / group;
+        if (!dev_tables) {
+            for (int m = 0; m < XS_NUM_MATERIALS; m++) {
+                if (b.count[m] <= 0) continue;
+                const bool is_dense = ctx->dense_min > 0 && b.count[m] >= (long)ctx->dense_min * d.P.n_gp;
+                if (is_dense != (dense == 1)) continue;
+                xs::WindowSegment &sgm = a.seg[a.n_seg++];
+                sgm.mat = m; sgm.first = d.h_mat_first[m]; sgm.j_begin = 0; sgm.j_end = ctx->num_nucs[m];
+                sgm.offset = b.offset[m];
+                sgm.count = (int)b.count[m];
+                sgm.group_begin = (int)groups;
+                const int group = dense ? xs::kDenseGroup : xs::kSortedGroup;
+                groups += (b.count[m] + group - 1) / group;
+            }
+            if (groups == 0) continue;
+        } else if (dense && ctx->dense_min <= 0) {
+            continue;
         }
-        if (groups == 0) continue;
+        a.dev_table = dev_tables ? dev_tables + dense : nullptr;
         a.n_groups = (int)groups;
         a.energy = b.energy;
         a.where = b.where;
@@ -572,8 +593,14 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
         CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem, threads);
         if (rc != XS_OK) return rc;
-        const long max_useful = (groups + warps - 1) / warps;
-        if (blocks > max_useful) blocks = (int)max_useful;
+        if (!dev_tables) {                                    // (a device-built table: the group count is not known here)
+            const long max_useful = (groups + warps - 1) / warps;
+            if (blocks > max_useful) blocks = (int)max_useful;
+        } else {
+            const long most = (b.total + (dense ? xs::kDenseGroup : xs::kSortedGroup) - 1) / (dense ? xs::kDenseGroup : xs::kSortedGroup) + XS_NUM_MATERIALS;
+            const long max_useful = (most + warps - 1) / warps;
+            if (blocks > max_useful) blocks = (int)max_useful;
+        }
         xs::BatchSink launch_sink = sink;
         launch_sink.batch_counter = d.dense_counter;          // group hand-out; the kernel leaves it zeroed
         k<<<blocks, threads, smem, d.stream>>>(d.P, a, launch_sink, d.conc);
@@ -713,6 +740,36 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
     d.pending.indirect = indirect;
     d.pending.sink = sink;
     return XS_OK;
+}
+
+// -k 6 without a host round trip: sort, then both lane-per-lookup launches with segment tables a
+// one-thread kernel derives from the histogram.  (The windowed sweep takes its slot ranges as kernel
+// arguments -- measured 5 % faster there -- so -k 4 / 5 keep the read-back.)
+int enqueue_sorted_nosync(xs_gpu_ctx *ctx, DeviceState &d, long base, long count, unsigned int *hist, xs::BatchSink sink,
+                          bool record_event, int table_slot)
+{
+    CUDA_TRY(cudaSetDevice(d.device));
+    uint32_t *sorted_perm = nullptr;
+    uint32_t *key[2] = { d.key[0] + base, d.key[1] + base }, *perm[2] = { d.perm[0] + base, d.perm[1] + base };
+    int rc = xs::sort_lookups(d.sort, key, perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
+    if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+    GroupedBatch b{};
+    b.indirect = ctx->fuse_gather != 0;
+    if (!b.indirect) {
+        const int blocks = (int)std::min<long>((count + 255) / 256, (long)d.sm_count * 16);
+        xs::xs_gather_kernel<<<blocks, 256, 0, d.stream>>>(sorted_perm, d.samp_e + base, d.samp_where + base, count,
+                                                          d.grp_e + base, d.grp_where + base);
+        CUDA_TRY(cudaGetLastError());
+        d.launches++;
+    }
+    if (record_event) CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+    b.pack = b.indirect && ctx->pack_samples ? d.samp_pack + base : nullptr;
+    b.energy = (b.indirect ? d.samp_e : d.grp_e) + base;
+    b.where = (b.indirect ? d.samp_where : d.grp_where) + base;
+    b.id = sorted_perm;
+    b.hist = hist;
+    b.total = count;
+    return launch_sorted(ctx, d, b, sink, d.seg_tables + 2 * table_slot);
 }
 
 // Back half: wait for the histogram, then sweep material by material.
@@ -880,6 +937,8 @@ int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long firs
                 src.mat_lo = 1; src.mat_hi = XS_NUM_MATERIALS - 1;
                 if (rc == XS_OK) rc = launch_event(ctx, d, src, sink, 1);
             }
+        } else if (kernel_id == 6 && ctx->sorted_kernel && ctx->device_segments && !d.bins_ready) {
+            rc = enqueue_sorted_nosync(ctx, d, 0, count, d.histogram, sink, first_pass, 0);
         } else {
             rc = enqueue_grouped_front(ctx, d, kernel_id, 0, count, d.histogram, d.counters + kCursorBase, sink, first_pass);
         }
@@ -1046,6 +1105,15 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->pack_samples = env_int("XSB200_PACK_SAMPLES", 1);
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
+    ctx->device_segments = env_int("XSB200_DEVICE_SEGMENTS", 1);
+    if (const char *split = getenv("XSB200_E2E_SPLIT")) {
+        int n = 0;
+        for (const char *p = split; *p && n < kMaxChunks; ) {
+            ctx->e2e_split[n++] = atoi(p);
+            while (*p >= '0' && *p <= '9') p++;
+            while (*p && !(*p >= '0' && *p <= '9')) p++;       // any separator
+        }
+    }
     {
         const char *arith = getenv("XSB200_ARITH");
         ctx->exact_arith = !(arith && (!strcmp(arith, "fused") || !strcmp(arith, "12")));
@@ -1194,22 +1262,42 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         sink.accum = d.accum;
         if (ctx->sweep && cnt > 0) {
             // Pipelined in chunks: the host->device copy of chunk c+1 (copy stream) overlaps the
-            // row search, sort and sweep of chunk c (compute stream).  Every chunk is a complete
-            // -k 6 (or, XSB200_E2E_KERNEL=4, -k 4) pipeline on its own slice of the buffers (one
-            // 64-byte histogram read-back per chunk; later copies keep running on the copy stream
-            // meanwhile).
-            int n_chunks = ctx->e2e_chunks ? ctx->e2e_chunks : (int)std::min<long>(kMaxChunks, std::max<long>(1, cnt / 8000000));
+            // row search, sort and lookup kernels of chunk c (compute stream).  Every chunk is a complete
+            // -k 6 (or, XSB200_E2E_KERNEL=4, -k 4) pipeline on its own slice of the buffers.
+            // Chunk schedule.  The call costs the copy of all samples plus whatever compute is not hidden
+            // behind it: the first chunk's copy has nothing to overlap with, the last chunk's compute nothing
+            // left to hide behind.  Many small chunks would shrink both ends -- but a chunk is a complete sorted
+            // pipeline, and what makes that pipeline fast is the DENSITY of the sorted lookups (lookups per grid
+            // interval: with a third of the samples fuel drops under the dense kernel's threshold and the lookup
+            // phase costs 1.5 x as much per lookup).  Measured on B200, 17 M lookups, 204 MB (profiles/r02_notes.md):
+            // 1 chunk 6.76 ms, 2 equal chunks 5.50, 3 chunks (28:40:32) 5.53, 4 chunks 5.9, 6 chunks 6.6, 8 chunks 7.2;
+            // the copy alone is 3.9 ms.  Nothing on the host waits between chunks (segment tables are built on
+            // the device).
+            static const int schedule[kMaxChunks + 1][kMaxChunks] = {
+                {}, {100}, {50, 50}, {28, 40, 32}, {22, 36, 27, 15}, {18, 27, 27, 17, 11}, {15, 25, 25, 17, 11, 7},
+                {13, 21, 23, 18, 12, 8, 5}, {11, 18, 21, 18, 13, 9, 6, 4} };
+            int n_chunks = ctx->e2e_chunks ? ctx->e2e_chunks : cnt >= 4000000 ? 2 : 1;
+            if (ctx->e2e_split[0] > 0) { n_chunks = 0; while (n_chunks < kMaxChunks && ctx->e2e_split[n_chunks] > 0) n_chunks++; }
+            const int *weights = ctx->e2e_split[0] > 0 ? ctx->e2e_split : schedule[n_chunks];
+            long bound[kMaxChunks + 1] = { 0 };
+            {
+                long total_w = 0, run = 0;
+                for (int c = 0; c < n_chunks; c++) total_w += weights[c];
+                for (int c = 0; c < n_chunks; c++) { run += weights[c]; bound[c + 1] = c + 1 == n_chunks ? cnt : cnt * run / total_w; }
+            }
+            const bool nosync = ctx->e2e_kernel == 6 && ctx->sorted_kernel && ctx->device_segments;
             CUDA_TRY(cudaEventRecord(d.ev_ready, d.stream));
             CUDA_TRY(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
             for (int c = 0; c < n_chunks; c++) {
-                const long c_lo = cnt * c / n_chunks, c_n = cnt * (c + 1) / n_chunks - c_lo;
+                const long c_lo = bound[c], c_n = bound[c + 1] - c_lo;
                 CUDA_TRY(cudaMemcpyAsync(d.samp_e + c_lo, h_energy + lo + c_lo, (size_t)c_n * sizeof(double), cudaMemcpyHostToDevice, d.copy_stream));
                 CUDA_TRY(cudaMemcpyAsync(d.samp_mat + c_lo, h_mat + lo + c_lo, (size_t)c_n * sizeof(int), cudaMemcpyHostToDevice, d.copy_stream));
                 CUDA_TRY(cudaEventRecord(d.ev_copy[c], d.copy_stream));
             }
             for (int c = 0; c < n_chunks && rc == XS_OK; c++) {
-                const long c_lo = cnt * c / n_chunks, c_n = cnt * (c + 1) / n_chunks - c_lo;
+                const long c_lo = bound[c], c_n = bound[c + 1] - c_lo;
                 CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_copy[c], 0));
+                if (c_n <= 0) continue;
                 const int blocks = (int)std::min<long>((c_n + 255) / 256, (long)d.sm_count * 16);
                 xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
                                                                  d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
@@ -1221,8 +1309,11 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                 if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
                 xs::BatchSink chunk_sink = sink;
                 chunk_sink.macro_out = h_macro_xs_out ? d.dump_macro + 5 * c_lo : nullptr;
-                rc = enqueue_grouped_lookup(ctx, d, ctx->e2e_kernel, c_lo, c_n, d.histogram + 16 * c, d.counters + kCursorBase + 16 * c,
-                                            chunk_sink, c == 0);
+                if (nosync)
+                    rc = enqueue_sorted_nosync(ctx, d, c_lo, c_n, d.histogram + 16 * c, chunk_sink, c == 0, c);
+                else
+                    rc = enqueue_grouped_lookup(ctx, d, ctx->e2e_kernel, c_lo, c_n, d.histogram + 16 * c, d.counters + kCursorBase + 16 * c,
+                                                chunk_sink, c == 0);
             }
         } else {
             CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
@@ -1378,7 +1469,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         if (d.stream) cudaStreamSynchronize(d.stream);
         cudaFree(d.hot_slab); cudaFree(d.index_grid); cudaFree(d.grid);
         cudaFree(d.mat_first); cudaFree(d.mat_nuc); cudaFree(d.mat_conc);
-        cudaFree(d.accum); cudaFree(d.counters); cudaFree(d.histogram); cudaFree(d.dense_counter);
+        cudaFree(d.accum); cudaFree(d.counters); cudaFree(d.histogram); cudaFree(d.dense_counter); cudaFree(d.seg_tables);
         cudaFree(d.samp_e); cudaFree(d.samp_mat);
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         cudaFree(d.bin_count); cudaFree(d.bin_chunk_sum);

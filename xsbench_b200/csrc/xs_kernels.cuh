@@ -438,7 +438,10 @@ struct WindowSegment {
     int  j_begin, j_end;       // nuclide window inside the material's list
 };
 
+struct SegTable;
 struct WindowArgs {
+    const SegTable *dev_table; // lane-per-lookup kernels: segments computed ON THE DEVICE from the material histogram
+                               // (xs_build_segments_kernel) -- the host then never waits for the histogram; null = seg[] below
     const double   *energy;    // energies grouped by material
     const uint32_t *where;     // same order: UEG row / hash bin
     const uint32_t *sample_id; // same order: original sample index (only for macro_xs dumps)
@@ -452,6 +455,51 @@ struct WindowArgs {
 };
 
 struct Quarter { double a, da, b, db; };
+
+// Segment table of one launch of the lane-per-lookup kernels, in device memory (see WindowArgs::dev_table).
+struct SegTable {
+    int n_groups, n_seg;
+    WindowSegment seg[kMaxSegments];
+};
+
+// The table a block works from: copied to shared memory from the device table or from the arguments.
+XS_DEV void load_seg_table(const WindowArgs &A, SegTable &T)
+{
+    if (A.dev_table) {
+        if (threadIdx.x == 0) { T.n_groups = A.dev_table->n_groups; T.n_seg = A.dev_table->n_seg; }
+        if (threadIdx.x < kMaxSegments) T.seg[threadIdx.x] = A.dev_table->seg[threadIdx.x];
+    } else {
+        if (threadIdx.x == 0) { T.n_groups = A.n_groups; T.n_seg = A.n_seg; }
+        if (threadIdx.x < kMaxSegments) T.seg[threadIdx.x] = A.seg[threadIdx.x];
+    }
+}
+
+struct MatShape { int first[kNumMaterials + 1]; int n_nuc[kNumMaterials]; };
+
+// Device-side replacement of the host loop in launch_sorted: which materials are dense (>= dense_min lookups
+// per grid interval), their slot ranges in the sorted batch (prefix of the histogram: the sort key's top
+// bits are the material) and their warp-groups.  One thread; 12 materials.
+__global__ void xs_build_segments_kernel(const unsigned int *hist, MatShape shape, long dense_threshold, int dense_group,
+                                         int sparse_group, SegTable *dense, SegTable *sparse)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    SegTable *tab[2] = { sparse, dense };
+    int groups[2] = { 0, 0 }, n_seg[2] = { 0, 0 };
+    long offset = 0;
+    for (int m = 0; m < kNumMaterials; m++) {
+        const long count = hist[m];
+        if (count > 0) {
+            const int d = dense_threshold > 0 && count >= dense_threshold;
+            WindowSegment &sgm = tab[d]->seg[n_seg[d]++];
+            sgm.offset = offset; sgm.count = (int)count; sgm.group_begin = groups[d];
+            sgm.mat = m; sgm.first = shape.first[m]; sgm.j_begin = 0; sgm.j_end = shape.n_nuc[m];
+            const int per = d ? dense_group : sparse_group;
+            groups[d] += (int)((count + per - 1) / per);
+        }
+        offset += count;
+    }
+    for (int d = 0; d < 2; d++) { tab[d]->n_groups = groups[d]; tab[d]->n_seg = n_seg[d]; }
+}
 
 
 // Asynchronous global->shared copies (LDGSTS): the next group's sample is fetched without
@@ -792,7 +840,7 @@ XS_DEV void record_step(const PairRecord &r, double e, double conc, double acc[5
 // ---- shared by the two lane-per-lookup kernels (xs_sorted_kernel, xs_dense_kernel) ----
 
 // The segment (material) a warp-group belongs to: warp-uniform, <= 11 steps.
-XS_DEV int segment_of_group(const WindowArgs &A, int g, int sg = 0)
+XS_DEV int segment_of_group(const SegTable &A, int g, int sg = 0)
 {
     while (sg + 1 < A.n_seg && g >= A.seg[sg + 1].group_begin) sg++;
     return sg;
@@ -872,7 +920,7 @@ XS_DEV void finish_lane_lookups(const WindowArgs &A, const BatchSink &sink, long
 }
 
 // Block's share of the verification sum, and (block 0) the lookups this launch completes.
-XS_DEV void finish_launch(const WindowArgs &A, const BatchSink &sink, unsigned int my_sum, unsigned long long *s_part)
+XS_DEV void finish_launch(const SegTable &A, const BatchSink &sink, unsigned int my_sum, unsigned long long *s_part)
 {
     const unsigned long long bs = block_sum(my_sum, s_part);
     if (threadIdx.x == 0) {
@@ -894,6 +942,8 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
     extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][staged record numbers][nuclide ids]
     uint32_t *s_rec = s_dyn + (kStaged ? kWarpsPerBlock * kRingBytes / 4 : 0);
     int *s_nuc = (int *)(s_rec + (kStaged ? kWarpsPerBlock * 32 * kLaneWords : 0));
+    __shared__ SegTable T;
+    load_seg_table(A, T);
     for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
     __syncthreads();
 
@@ -905,9 +955,9 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + (kStaged ? warp * kRingBytes : 0);
 
     // groups are handed out in order by an atomic counter (see warp_next_group)
-    for (int g = warp_next_group(sink, lane); g < A.n_groups; g = warp_next_group(sink, lane)) {
-        const int sg = segment_of_group(A, g);
-        const WindowSegment &S = A.seg[sg];
+    for (int g = warp_next_group(sink, lane); g < T.n_groups; g = warp_next_group(sink, lane)) {
+        const int sg = segment_of_group(T, g);
+        const WindowSegment &S = T.seg[sg];
         const int first_in_seg = (g - S.group_begin) * kSortedGroup + lane * kPerLane;
         const long t0 = S.offset + first_in_seg;
         double e[kPerLane];
@@ -1078,7 +1128,7 @@ xs_sorted_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
         finish_lane_lookups<kPerLane>(A, sink, t0, on, acc, my_sum);
     }
     warp_groups_done(sink, lane);
-    finish_launch(A, sink, my_sum, s_part);
+    finish_launch(T, sink, my_sum, s_part);
 }
 
 // (xs_dense_kernel, the kernel for dense segments, lives in xs_dense.cuh)
