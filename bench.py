@@ -282,7 +282,7 @@ def measure_traffic(args, device_index: int):
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
-           "--kernel-name", "regex:xs_(dense|sorted|event|window)_kernel", "--csv", "--log-file", log,
+           "--kernel-name", "regex:xs_(dense|sorted|event|window|tile)_kernel", "--csv", "--log-file", log,
            sys.executable, os.path.abspath(__file__), "--traffic-probe", "--size", args.size, "--lookups", str(args.lookups)]
     try:
         p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
@@ -306,7 +306,9 @@ def measure_traffic(args, device_index: int):
         n_window = sum(1 for (i, n), m in launches if "xs_window_kernel" in n)
         dense_b, dense_t = last_of("xs_dense_kernel")
         sparse_b, sparse_t = last_of("xs_sorted_kernel")
-        event_b, event_t = last_of("xs_event_kernel")
+        event_b, event_t = last_of("xs_tile_kernel")
+        if event_b is None:
+            event_b, event_t = last_of("xs_event_kernel")
         window_b, window_t = last_of("xs_window_kernel", n_window)
         return {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on a subprocess of this bench (one pass each of -k 6 / -k 0 / -k 4, same problem), this run",
                 "k6_lookup_phase_bytes": (dense_b or 0.0) + (sparse_b or 0.0) if dense_b is not None or sparse_b is not None else None,
@@ -643,14 +645,14 @@ def main():
             roofline = {"bound": "hbm", "achieved": alg_step / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_step / kernel_s / 1e9 / hbm_peak, "traffic": dram, "traffic_source": (traffic or {}).get("source"),
                         "kernel_ms": 1e3 * kernel_s, "peak_source": peak_src, "hbm": hbm_view(kernel_s, dram),
-                        "kernel": "xs_event_kernel<unionized>" if args.kernel < 4 else "xs_window_kernel<unionized> (all launches of one step)"}
+                        "kernel": "xs_tile_kernel<unionized>" if args.kernel < 4 else "xs_window_kernel<unionized> (all launches of one step)"}
         if "k0" in variants:
             secs = variants["k0"]["lookup_phase_ms"] * 1e-3
             variants["k0"]["roofline"] = dict(bound="hbm", achieved=alg_step / secs / 1e9, peak=hbm_peak, unit="GB/s",
                                               frac=alg_step / secs / 1e9 / hbm_peak, traffic=k0_bytes,
                                               traffic_over_algorithmic=(k0_bytes / alg_step) if k0_bytes else None,
                                               hbm_achieved_frac=(k0_bytes / secs / 1e9 / hbm_peak) if k0_bytes else None,
-                                              kernel="xs_event_kernel<unionized> (one fused in-order launch)")
+                                              kernel="xs_tile_kernel<unionized> (one launch: tiles grouped in shared memory, windowed sweep, grid barrier per round)")
         if "k4" in variants and k4_bytes:
             secs = variants["k4"]["lookup_phase_ms"] * 1e-3
             variants["k4"]["roofline"] = dict(bound="l1/l2 gather (see DESIGN.md 5.1b)", traffic=k4_bytes,

@@ -21,6 +21,7 @@
 #include "xs_gpu.h"
 #include "xs_kernels.cuh"
 #include "xs_dense.cuh"
+#include "xs_tile.cuh"
 #include "xs_sort.cuh"
 #include "xs_generate.cuh"
 
@@ -149,6 +150,9 @@ struct xs_gpu_ctx {
     int e2e_kernel = 6;                    // xs_gpu_lookup_samples: 6 = sort + lane-per-lookup kernel, 4 = partition + windowed sweep
     int sorted_kernel = 1;                 // -k 6: lane-per-lookup kernel on the energy-sorted batch (0 = windowed sweep)
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
+    int tile = 1;                          // -k 0..3 / xs_gpu_dump: xs_tile_kernel (tiles grouped in shared memory, windowed sweep, grid
+                                           // barrier per round); 0 = round 1's xs_event_kernel (XSB200_TILE=0)
+    int tile_barrier = 1;                  // XSB200_TILE_BARRIER=0: no grid barrier between rounds (plain launch)
     int device_segments = 1;               // -k 6 / host-sample pipeline: segment tables built on the device, no histogram read-back
     int e2e_split[kMaxChunks] = {};        // XSB200_E2E_SPLIT: chunk sizes of a host-sample call, in percent (0 = built-in schedule)
     int exact_arith = 1;                   // xs_dense_kernel: 1 = the reference's roundings (24 FP64 operations per (lookup, nuclide), macro_xs
@@ -472,10 +476,41 @@ int ensure_dump_buffer(DeviceState &d, long n)
 // ---------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------
+typedef void (*TileKernel)(const xs::Problem, const xs::BatchSource, const xs::BatchSink, const xs::ConcTable, int, int);
+
+// The in-order variants in one launch with deliberate L2 locality (xs_tile.cuh).  The grid barrier needs
+// every block resident: cooperative launch, grid = occupancy x SMs.
+int launch_tile(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs::BatchSink sink, int counter_slot)
+{
+    static const TileKernel table[3] = { xs::xs_tile_kernel<xs::kUnionized>, xs::xs_tile_kernel<xs::kNuclide>, xs::xs_tile_kernel<xs::kHash> };
+    TileKernel k = table[ctx->grid_type];
+    const size_t smem = sizeof(xs::TileShared) + (size_t)d.P.mat_total * sizeof(int) + (XS_NUM_MATERIALS + 1) * sizeof(int);
+    CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = 0;
+    int rc = persistent_grid(ctx, d, (const void *)k, &blocks, (long)smem);
+    if (rc != XS_OK) return rc;
+    const long n_tiles = (src.count + xs::kTile - 1) / xs::kTile;
+    if (blocks > n_tiles) blocks = (int)n_tiles;
+    sink.batch_counter = d.counters + counter_slot;           // the round barrier's arrival counter (zeroed per pass)
+    const int quantum = 2 * xs::kSweepUnroll;
+    int window = std::max(quantum, std::min(ctx->window, 32) / quantum * quantum);
+    int use_barrier = ctx->tile_barrier;
+    if (use_barrier) {
+        void *args[] = { (void *)&d.P, (void *)&src, (void *)&sink, (void *)&d.conc, (void *)&window, (void *)&use_barrier };
+        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k, dim3(blocks), dim3(xs::kBlockThreads), args, smem, d.stream));
+    } else {
+        k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, src, sink, d.conc, window, use_barrier);
+        CUDA_TRY(cudaGetLastError());
+    }
+    d.launches++;
+    return XS_OK;
+}
+
 int launch_event(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs::BatchSink sink,
                  int counter_slot)
 {
     if (src.count <= 0) return XS_OK;
+    if (ctx->tile && !sink.fwd_out) return launch_tile(ctx, d, src, sink, counter_slot);
     EventKernel k = event_kernel(ctx->grid_type, ctx->gather);
     int blocks = 0;
     int rc = persistent_grid(ctx, d, (const void *)k, &blocks);
@@ -1106,6 +1141,8 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
     ctx->device_segments = env_int("XSB200_DEVICE_SEGMENTS", 1);
+    ctx->tile = env_int("XSB200_TILE", 1);
+    ctx->tile_barrier = env_int("XSB200_TILE_BARRIER", 1);
     if (const char *split = getenv("XSB200_E2E_SPLIT")) {
         int n = 0;
         for (const char *p = split; *p && n < kMaxChunks; ) {

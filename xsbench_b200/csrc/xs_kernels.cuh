@@ -582,6 +582,70 @@ XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1]
     }
 }
 
+// One window of one warp-group: 8 lookups x 4 lanes sweep the nuclides nucs[0..jn) (jn <= kMaxWindow).
+// `e` / `where32` are the slot's sample (the same on its 4 lanes), `ci` the index of the window's
+// first concentration in C.v; acc_x / acc_y carry the two channels of lane `quarter` in and out.
+// Shared by xs_window_kernel (lookups grouped in global memory, one window per launch) and
+// xs_tile_kernel (-k 0..3: lookups grouped per tile in shared memory, all windows in one launch).
+template <int GRID>
+XS_DEV void window_sweep_group(const Problem &P, const ConcTable &C, uint32_t (*rec_rows)[kMaxWindow + 1], const int *nucs,
+                               int jn, int ci, int slots_on, uint32_t where32, double e, int lane, double &acc_x, double &acc_y)
+{
+    const int slot = lane >> 2, quarter = lane & 3;
+    const int f_src = lane | 3;
+    const double2 *my_pairs = P.pairs + 2 * quarter;
+    const int n_steps = (jn + 2 * kSweepUnroll - 1) / (2 * kSweepUnroll) * (2 * kSweepUnroll);
+    // ---- resolve the record numbers of the window for the 8 lookups of this warp ------
+    __syncwarp();
+    {
+        if (n_steps <= 4)       stage_records<GRID, 2>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+        else if (n_steps <= 8)  stage_records<GRID, 3>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+        else if (n_steps <= 16) stage_records<GRID, 4>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+        else {
+            stage_records<GRID, 5>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+            if (n_steps > 32)   // a folded remainder: steps 32..32 + 2^kFoldShift - 1
+                stage_records<GRID, kFoldShift>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane, 32);
+        }
+    }
+    __syncwarp();
+
+    // ---- software-pipelined gather: no predication, padded steps multiply by 0 ----------
+    const uint32_t *my_rec = rec_rows[slot];
+    Quarter A0[kSweepUnroll], A1[kSweepUnroll];
+#pragma unroll
+    for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
+    int j0 = 0;
+    double e0 = e, e1 = e;
+    for (; j0 + 2 * kSweepUnroll < n_steps; j0 += 2 * kSweepUnroll) {
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            sweep_step(A0[u], e0, C.v[ci + j0 + u], f_src, acc_x, acc_y);
+        e1 = order_after(e, acc_x);
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            sweep_step(A1[u], e1, C.v[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+        e0 = order_after(e, acc_x);
+    }
+    {   // last iteration: nothing left to prefetch
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            sweep_step(A0[u], e0, C.v[ci + j0 + u], f_src, acc_x, acc_y);
+        e1 = order_after(e, acc_x);
+#pragma unroll
+        for (int u = 0; u < kSweepUnroll; u++)
+            sweep_step(A1[u], e1, C.v[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
+    }
+}
+
 template <int GRID>
 __global__ void __launch_bounds__(kBlockThreads, XS_SWEEP_BLOCKS)
 xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink, const ConcTable C)
@@ -597,8 +661,6 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = lane >> 2, quarter = lane & 3;
-    const int f_src = lane | 3;
-    const double2 *my_pairs = P.pairs + 2 * quarter;
     const int warp_global = blockIdx.x * kWarpsPerBlock + warp;
     const int warp_stride = gridDim.x * kWarpsPerBlock;
     unsigned int my_sum = 0;                                 // per thread: far below 2^32
@@ -629,7 +691,6 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
         const long t = A.seg[sg].offset + in_seg;                // global slot
         const bool on = in_seg < A.seg[sg].count;
         const int jn = S.j_end - S.j_begin;
-        const int n_steps = (jn + 2 * kSweepUnroll - 1) / (2 * kSweepUnroll) * (2 * kSweepUnroll);
 
         cp_async_wait_all();
         const double e = s_next_e[threadIdx.x];
@@ -642,58 +703,9 @@ xs_window_kernel(const Problem P, const WindowArgs A, const BatchSink sink, cons
             acc_y = part.y;
         }
 
-        // ---- resolve the record numbers of the window for the 8 lookups of this warp ------
-        __syncwarp();
-        {
-            const int slots_on = min(kSweepSlots, A.seg[sg].count - (g - A.seg[sg].group_begin) * kSweepSlots);
-            const int *nucs = s_nuc + S.first + S.j_begin;
-            if (n_steps <= 4)       stage_records<GRID, 2>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
-            else if (n_steps <= 8)  stage_records<GRID, 3>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
-            else if (n_steps <= 16) stage_records<GRID, 4>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
-            else {
-                stage_records<GRID, 5>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane);
-                if (n_steps > 32)   // a folded remainder: steps 32..32 + 2^kFoldShift - 1
-                    stage_records<GRID, kFoldShift>(P, s_rec[warp], nucs, jn, n_steps, slots_on, where32, e, lane, 32);
-            }
-        }
-        __syncwarp();
-
-        // ---- software-pipelined gather: no predication, padded steps multiply by 0 ----------
-        const uint32_t *my_rec = s_rec[warp][slot];
-        const int ci = C.first[S.mat] + S.j_begin;
-        Quarter A0[kSweepUnroll], A1[kSweepUnroll];
-#pragma unroll
-        for (int u = 0; u < kSweepUnroll; u++) A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[u]);
-        int j0 = 0;
-        double e0 = e, e1 = e;
-        for (; j0 + 2 * kSweepUnroll < n_steps; j0 += 2 * kSweepUnroll) {
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A0[u], e0, C.v[ci + j0 + u], f_src, acc_x, acc_y);
-            e1 = order_after(e, acc_x);
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                A0[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + 2 * kSweepUnroll + u]);
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A1[u], e1, C.v[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
-            e0 = order_after(e, acc_x);
-        }
-        {   // last iteration: nothing left to prefetch
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                A1[u] = ldg_quarter(my_pairs + 8 * (long)my_rec[j0 + kSweepUnroll + u]);
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A0[u], e0, C.v[ci + j0 + u], f_src, acc_x, acc_y);
-            e1 = order_after(e, acc_x);
-#pragma unroll
-            for (int u = 0; u < kSweepUnroll; u++)
-                sweep_step(A1[u], e1, C.v[ci + j0 + kSweepUnroll + u], f_src, acc_x, acc_y);
-        }
+        window_sweep_group<GRID>(P, C, s_rec[warp], s_nuc + S.first + S.j_begin, jn, C.first[S.mat] + S.j_begin,
+                                 min(kSweepSlots, A.seg[sg].count - (g - A.seg[sg].group_begin) * kSweepSlots), where32, e, lane,
+                                 acc_x, acc_y);
 
         if (!A.last_window) {
             if (on && quarter < 3) A.partial[3 * t + quarter] = make_double2(acc_x, acc_y);
