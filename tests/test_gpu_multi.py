@@ -60,6 +60,31 @@ def test_in_process_energy_bands(monkeypatch):
         xs.free_simulation_data(sd)
 
 
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_in_process_history_and_host_samples_on_several_gpus(monkeypatch):
+    """History mode and xs_gpu_lookup_samples with one process driving 2 GPUs: particles / samples split (grid
+    replicated), and -- XSB200_BANDS=2 -- every GPU stepping every particle, looking up its energy band and the
+    feedback bytes all-reduced (NCCL, uint8) every generation."""
+    import numpy as np
+    orc = ol.OracleProblem(68, 1000, 0, 10000)
+    want_hist = orc.history(0, 3000, 34, os.cpu_count() or 1)
+    rng = np.random.default_rng(31)
+    e = rng.random(50_000); m = rng.integers(0, 12, len(e)).astype(np.int32)
+    want_v, want_macro = orc.lookup_samples(e, m)
+    orc.close()
+    hist = xs.make_inputs(size="small", method="history", grid="unionized", gridpoints=1000, particles=3000, lookups=34)
+    for bands in (None, "2"):
+        if bands:
+            monkeypatch.setenv("XSB200_BANDS", bands)
+        sd = xs.materials_only(hist)
+        with xs.move_simulation_data_to_device(hist, sd, n_gpus=2) as gpu:
+            res = gpu.run(hist)
+            assert res.n_gpus == 2 and res.n_lookups == 34 * 3000 and res.verification == want_hist == 309181
+            r2, macro = gpu.lookup_samples(e, m, want_macro_xs=True)
+            assert r2.verification == want_v and r2.n_lookups == len(e) and np.array_equal(macro, want_macro)
+        xs.free_simulation_data(sd)
+
+
 @pytest.mark.slow
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
 def test_xxl_unionized_across_gpus():

@@ -355,12 +355,46 @@ def test_energy_bands_sum_to_the_whole(monkeypatch, device_init):
                 gpu._check(gpu._lib.xs_gpu_read_array(gpu._ctx, 2, r_lo * info.n_isotopes * 4, rows.nbytes, rows.ctypes.data))
                 full = xs.simulation_arrays(inp, sd)["index_grid"]
                 assert np.array_equal(rows, full[r_lo * info.n_isotopes:r_hi * info.n_isotopes])
+            # history mode needs all bands in one context (they exchange the particles' feedback each generation)
             with pytest.raises(xs.XSGpuError):
                 gpu.run(xs.make_inputs(size="small", method="history", grid="unionized", gridpoints=1000, particles=100, lookups=5))
             total_v += r6.verification
             total_n += r6.n_lookups
         xs.free_simulation_data(sd)
     assert total_n == n and total_v == 302880
+
+
+def test_energy_bands_host_samples_and_dump(monkeypatch):
+    """xs_gpu_lookup_samples and xs_gpu_dump on band-sharded contexts: every band takes all samples, performs
+    the lookups of its rows and leaves zeros elsewhere; the bands' checksums, counts and macro_xs rows add up
+    to the un-sharded result (bit for bit: a sum with zeros)."""
+    bands = 3
+    rng = np.random.default_rng(29)
+    e = rng.random(40_000); m = rng.integers(0, 12, len(e)).astype(np.int32)
+    orc = ol.OracleProblem(68, 1000, 0, 10000)
+    want_v, want_macro = orc.lookup_samples(e, m)
+    _, oe, om, omacro, oam = orc.event_dump(5, 3000)
+    total_v = total_n = 0
+    macro_sum = np.zeros((len(e), 5)); dump_sum = np.zeros((3000, 5)); performed = np.zeros(3000, np.int64)
+    for b in range(bands):
+        monkeypatch.setenv("XSB200_BANDS", str(bands))
+        monkeypatch.setenv("XSB200_BAND_INDEX", str(b))
+        inp = xs.make_inputs(size="small", method="event", grid="unionized", lookups=1000, gridpoints=1000, kernel_id=6)
+        sd = xs.materials_only(inp)
+        with xs.move_simulation_data_to_device(inp, sd) as gpu:
+            res, macro = gpu.lookup_samples(e, m, want_macro_xs=True)
+            assert 0 < res.n_lookups < len(e)
+            assert np.count_nonzero(macro.any(axis=1)) == res.n_lookups
+            total_v += res.verification; total_n += res.n_lookups; macro_sum += macro
+            de, dm, dx, da = gpu.dump(5, 3000)
+            assert np.array_equal(de, oe) and np.array_equal(dm, om)            # sampling does not depend on the band
+            mine = da >= 0
+            assert np.array_equal(da[mine], oam[mine]) and not dx[~mine].any()
+            dump_sum += dx; performed += mine
+        xs.free_simulation_data(sd)
+    orc.close()
+    assert total_v == want_v and total_n == len(e) and np.array_equal(macro_sum, want_macro)
+    assert np.all(performed == 1) and float(np.max(np.abs(dump_sum - omacro) / np.abs(omacro))) <= REL_TOL
 
 
 # ---- device-side generator: byte-identical to the host generator --------------------------------------------

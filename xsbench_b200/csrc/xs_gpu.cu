@@ -982,59 +982,107 @@ int enqueue_event_pass(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long firs
 }
 
 // History mode by generations: every generation is an event-style batch (all live particles'
-// current lookups), regrouped by material and swept like -k 4; the feedback that makes the
-// reference's inner loop dependent (n_forward) travels through one byte per particle.
-int enqueue_history_generations(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n_particles, int lookups)
+// current lookups); the feedback that makes the reference's inner loop dependent (n_forward) travels
+// through one byte per particle.  A generation runs the sorted pipeline without a host round trip
+// (xs_history_step_kernel -> radix sort -> segment tables -> lane-per-lookup kernels), or, with
+// XSB200_SORTED_KERNEL=0 / XSB200_DEVICE_SEGMENTS=0, round 1's partition + windowed sweep.  Several GPUs
+// of one process are fed generation by generation, device by device, so they run side by side.
+// Energy-band sharding: every device steps every particle, looks up the ones whose row lies in its band
+// and the per-particle feedback bytes are summed over the devices (NCCL all-reduce, uint8) before the
+// next generation -- the one place where this path has a collective in the data path.
+int xs_multi_allreduce_bytes(xs_gpu_ctx *ctx, size_t n_bytes);
+
+int enqueue_history_all(xs_gpu_ctx *ctx, long first_particle, long n_particles, int lookups)
 {
-    int rc = XS_OK;
-    for (long done = 0; done < n_particles && rc == XS_OK; done += ctx->max_pass) {
-        const long n = std::min(n_particles - done, ctx->max_pass);
-        if ((rc = ensure_sample_buffers(d, n, true)) != XS_OK) return rc;
-        const int blocks = (int)std::min<long>((n + 255) / 256, (long)d.sm_count * 16);
-        for (int gen = 0; gen < lookups && rc == XS_OK; gen++) {
-            CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
-            CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
-            xs::xs_history_step_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_particle + done, n, lookups, gen,
-                                                                   d.hist_seed, d.hist_fwd, d.samp_e, d.samp_mat,
-                                                                   d.samp_where, d.histogram);
-            CUDA_TRY(cudaGetLastError());
-            d.launches++;
+    const int n = (int)ctx->dev.size();
+    const bool bands = ctx->n_bands > 1;
+    if (bands && n != ctx->n_bands)
+        return set_error(XS_ERR_UNSUPP, "xs_gpu_run: history mode on an energy-band-sharded grid needs all bands in one context "
+                                        "(the bands exchange the particles' feedback every generation)");
+    long lo[8], cnt[8];
+    for (int g = 0; g < n; g++) {
+        DeviceState &d = ctx->dev[g];
+        lo[g] = bands ? first_particle : first_particle + n_particles * g / n;
+        cnt[g] = bands ? n_particles : first_particle + n_particles * (g + 1) / n - lo[g];
+        CUDA_TRY(cudaSetDevice(d.device));
+        d.launches = 0;
+        CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
+    }
+    if (!ctx->sweep) {
+        // warp per particle, all lookups of a particle in one go (round 1's first version; kept for comparison)
+        for (int g = 0; g < n; g++) {
+            DeviceState &d = ctx->dev[g];
+            if (cnt[g] <= 0) continue;
+            CUDA_TRY(cudaSetDevice(d.device));
+            HistoryKernel k = history_kernel(ctx->grid_type, ctx->gather);
+            int blocks = 0;
+            int rc = persistent_grid(ctx, d, (const void *)k, &blocks);
+            if (rc != XS_OK) return rc;
+            const long max_useful = (cnt[g] + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
+            if (blocks > max_useful) blocks = (int)max_useful;
             xs::BatchSink sink{};
             sink.accum = d.accum;
-            sink.fwd_out = d.hist_fwd;
-            rc = enqueue_grouped_lookup(ctx, d, 4, 0, n, d.histogram, d.counters + kCursorBase, sink, false);
+            sink.batch_counter = d.counters;
+            k<<<blocks, xs::kBlockThreads, ctx->smem_bytes, d.stream>>>(d.P, lo[g], cnt[g], lookups, sink);
+            CUDA_TRY(cudaGetLastError());
+            d.launches++;
+        }
+    } else {
+        long most = 0;
+        for (int g = 0; g < n; g++) most = std::max(most, cnt[g]);
+        // The sorted pipeline pays when a generation is dense enough for xs_dense_kernel (fuel, 13.9 % of the
+        // lookups, at >= dense_min lookups per grid interval: 5.2 M particles at "large"); below that the
+        // partition + windowed sweep is faster (500 k particles x 34: 14.3 vs 18.8 ms).  Band sharding needs
+        // the sorted pipeline (it is the one that drops the other bands' lookups).
+        const bool dense_enough = ctx->dense_min > 0 && 0.139 * (double)std::min(most, ctx->max_pass) >= (double)ctx->dense_min * (double)ctx->n_gp;
+        const bool nosync = ctx->sorted_kernel && ctx->device_segments && (bands || dense_enough || env_int("XSB200_HISTORY_SORTED", 0));
+        if (bands && !nosync)
+            return set_error(XS_ERR_UNSUPP, "xs_gpu_run: history mode on an energy-band-sharded grid needs the sorted pipeline (default knobs)");
+        for (long done = 0; done < most; done += ctx->max_pass) {
+            long pass[8];
+            for (int g = 0; g < n; g++) {
+                pass[g] = std::max<long>(0, std::min(cnt[g] - done, ctx->max_pass));
+                if (pass[g] > 0) { int rc = ensure_sample_buffers(ctx->dev[g], pass[g], true); if (rc != XS_OK) return rc; }
+            }
+            for (int gen = 0; gen < lookups; gen++) {
+                for (int g = 0; g < n; g++) {
+                    DeviceState &d = ctx->dev[g];
+                    const long np = pass[g];
+                    if (np <= 0) continue;
+                    CUDA_TRY(cudaSetDevice(d.device));
+                    CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
+                    CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
+                    const int blocks = (int)std::min<long>((np + 255) / 256, (long)d.sm_count * 16);
+                    xs::xs_history_step_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, lo[g] + done, np, lookups, gen,
+                                                                           d.hist_seed, d.hist_fwd, d.samp_e, d.samp_mat, d.samp_where,
+                                                                           d.histogram, nosync ? d.key[0] : nullptr,
+                                                                           nosync && ctx->pack_samples ? d.samp_pack : nullptr,
+                                                                           bands ? (uint32_t)d.row0 : 0u, bands ? (uint32_t)d.row1 : 0xffffffffu);
+                    CUDA_TRY(cudaGetLastError());
+                    d.launches++;
+                    if (bands) CUDA_TRY(cudaMemsetAsync(d.hist_fwd, 0, (size_t)np, d.stream));   // each band fills in its own particles
+                    xs::BatchSink sink{};
+                    sink.accum = d.accum;
+                    sink.fwd_out = d.hist_fwd;
+                    int rc = nosync ? enqueue_sorted_nosync(ctx, d, 0, np, d.histogram, sink, false, 0)
+                                    : enqueue_grouped_lookup(ctx, d, 4, 0, np, d.histogram, d.counters + kCursorBase, sink, false);
+                    if (rc != XS_OK) return rc;
+                }
+                if (bands && gen + 1 < lookups) {
+                    int rc = xs_multi_allreduce_bytes(ctx, (size_t)pass[0]);
+                    if (rc != XS_OK) return rc;
+                }
+            }
         }
     }
-    return rc;
-}
-
-int enqueue_history(xs_gpu_ctx *ctx, DeviceState &d, long first_particle, long n_particles, int lookups)
-{
-    CUDA_TRY(cudaSetDevice(d.device));
-    d.launches = 0;
-    CUDA_TRY(cudaEventRecord(d.ev[EV_START], d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
-    CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
-    CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
-    CUDA_TRY(cudaEventRecord(d.ev[EV_SORTED], d.stream));
-    if (n_particles > 0 && ctx->sweep) {
-        int rc = enqueue_history_generations(ctx, d, first_particle, n_particles, lookups);
-        if (rc != XS_OK) return rc;
-    } else if (n_particles > 0) {
-        HistoryKernel k = history_kernel(ctx->grid_type, ctx->gather);
-        int blocks = 0;
-        int rc = persistent_grid(ctx, d, (const void *)k, &blocks);
-        if (rc != XS_OK) return rc;
-        const long max_useful = (n_particles + xs::kWarpsPerBlock - 1) / xs::kWarpsPerBlock;
-        if (blocks > max_useful) blocks = (int)max_useful;
-        xs::BatchSink sink{};
-        sink.accum = d.accum;
-        sink.batch_counter = d.counters;
-        k<<<blocks, xs::kBlockThreads, ctx->smem_bytes, d.stream>>>(d.P, first_particle, n_particles, lookups, sink);
-        CUDA_TRY(cudaGetLastError());
-        d.launches++;
+    for (int g = 0; g < n; g++) {
+        CUDA_TRY(cudaSetDevice(ctx->dev[g].device));
+        CUDA_TRY(cudaEventRecord(ctx->dev[g].ev[EV_LOOKED_UP], ctx->dev[g].stream));
     }
-    CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
     return XS_OK;
 }
 
@@ -1212,9 +1260,9 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
             rc = ensure_sample_buffers(ctx->dev[g], std::min(per_gpu, ctx->max_pass), in->kernel_id >= 4 || ctx->n_bands > 1,
                                        ctx->bin_bits);
     }
-    if (rc == XS_OK && in->simulation_method == XS_HISTORY_BASED && in->particles > 0 && ctx->sweep && ctx->n_bands == 1) {
+    if (rc == XS_OK && in->simulation_method == XS_HISTORY_BASED && in->particles > 0 && ctx->sweep) {
         // history mode works on one generation (= all particles) at a time
-        const long per_gpu = ((long)in->particles + n_gpus - 1) / n_gpus;
+        const long per_gpu = ctx->n_bands > 1 ? (long)in->particles : ((long)in->particles + n_gpus - 1) / n_gpus;
         for (int g = 0; g < n_gpus && rc == XS_OK; g++) rc = ensure_sample_buffers(ctx->dev[g], per_gpu, true);
     }
     if (rc == XS_OK && n_gpus > 1) rc = xs_multi_init(ctx);
@@ -1246,9 +1294,6 @@ int xs_gpu_run_range(xs_gpu_ctx *ctx, const Inputs *in, long first_id, long coun
     if (in->grid_type != ctx->grid_type || in->n_isotopes != ctx->n_iso || in->n_gridpoints != ctx->n_gp)
         return set_error(XS_ERR_ARG, "xs_gpu_run: Inputs do not match the problem uploaded by xs_gpu_init");
 
-    if (ctx->n_bands > 1 && !event)
-        return set_error(XS_ERR_UNSUPP, "xs_gpu_run: history mode is not available on an energy-band-sharded grid");
-
     const double t0 = wall_seconds();
     const int n = (int)ctx->dev.size();
     if (event) {
@@ -1257,11 +1302,8 @@ int xs_gpu_run_range(xs_gpu_ctx *ctx, const Inputs *in, long first_id, long coun
         int rc = enqueue_event_all(ctx, ctx->n_bands > 1 ? 6 : in->kernel_id, first_id, count);
         if (rc != XS_OK) return rc;
     } else {
-        for (int g = 0; g < n; g++) {
-            const long lo = first_id + count * g / n, hi = first_id + count * (g + 1) / n;
-            int rc = enqueue_history(ctx, ctx->dev[g], lo, hi - lo, in->lookups);
-            if (rc != XS_OK) return rc;
-        }
+        int rc = enqueue_history_all(ctx, first_id, count, in->lookups);
+        if (rc != XS_OK) return rc;
     }
     return finish_run(ctx, res, t0);
 }
@@ -1279,13 +1321,18 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
     DeviceGuard restore_device;
     if (!ctx || !h_energy || !h_mat || !res || n < 0)
         return set_error(XS_ERR_ARG, "xs_gpu_lookup_samples: bad argument");
-    if (ctx->n_bands > 1)
-        return set_error(XS_ERR_UNSUPP, "xs_gpu_lookup_samples: not available on an energy-band-sharded grid");
+    // Energy-band sharding: every device takes ALL samples and looks up those whose unionized row lies in
+    // its band (a single-GPU context holding one band returns that band's share: the caller adds the
+    // contexts up, like for xs_gpu_run; macro_xs rows of other bands' lookups stay zero).
+    const bool bands = ctx->n_bands > 1;
+    if (bands && !(ctx->sweep && ctx->e2e_kernel == 6 && ctx->sorted_kernel && ctx->device_segments))
+        return set_error(XS_ERR_UNSUPP, "xs_gpu_lookup_samples: an energy-band-sharded grid needs the sorted pipeline (default knobs)");
     const double t0 = wall_seconds();
     const int ng = (int)ctx->dev.size();
     for (int g = 0; g < ng; g++) {
         DeviceState &d = ctx->dev[g];
-        const long lo = n * g / ng, cnt = n * (g + 1) / ng - lo;
+        const long lo = bands ? 0 : n * g / ng, cnt = bands ? n : n * (g + 1) / ng - lo;
+        const uint32_t band_lo = bands ? (uint32_t)d.row0 : 0u, band_hi = bands ? (uint32_t)d.row1 : 0xffffffffu;
         int rc = ensure_sample_buffers(d, cnt, ctx->sweep != 0);
         if (rc == XS_OK && h_macro_xs_out) rc = ensure_dump_buffer(d, cnt);
         if (rc != XS_OK) return rc;
@@ -1297,6 +1344,8 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
         xs::BatchSink sink{};
         sink.accum = d.accum;
+        if (bands && h_macro_xs_out && cnt > 0)
+            CUDA_TRY(cudaMemsetAsync(d.dump_macro, 0, (size_t)cnt * 5 * sizeof(double), d.stream));
         if (ctx->sweep && cnt > 0) {
             // Pipelined in chunks: the host->device copy of chunk c+1 (copy stream) overlaps the
             // row search, sort and lookup kernels of chunk c (compute stream).  Every chunk is a complete
@@ -1340,7 +1389,7 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                                                                  d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
                                                                  d.histogram + 16 * c,
                                                                  ctx->e2e_kernel == 6 && ctx->pack_samples ? d.samp_pack + c_lo : nullptr,
-                                                                 d.accum + 2);
+                                                                 d.accum + 2, band_lo, band_hi);
                 CUDA_TRY(cudaGetLastError());
                 d.launches++;
                 if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
@@ -1370,19 +1419,28 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
             rc = launch_event(ctx, d, src, sink, 0);
         }
         if (rc != XS_OK) return rc;
-        if (h_macro_xs_out)
+        if (h_macro_xs_out && (!bands || g == 0))
             CUDA_TRY(cudaMemcpyAsync(h_macro_xs_out + 5 * lo, d.dump_macro, (size_t)cnt * 5 * sizeof(double), cudaMemcpyDeviceToHost, d.stream));
         CUDA_TRY(cudaEventRecord(d.ev[EV_LOOKED_UP], d.stream));
     }
     int rc = finish_run(ctx, res, t0);
     if (rc != XS_OK) return rc;
+    if (bands && h_macro_xs_out && ng > 1 && n > 0) {
+        // every lookup was performed by exactly one band, the others left zeros: add the bands up (exact)
+        std::vector<double> part((size_t)n * 5);
+        for (int g = 1; g < ng; g++) {
+            CUDA_TRY(cudaSetDevice(ctx->dev[g].device));
+            CUDA_TRY(cudaMemcpy(part.data(), ctx->dev[g].dump_macro, part.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < part.size(); i++) h_macro_xs_out[i] += part[i];
+        }
+    }
     unsigned long long rejected = 0;
     for (int g = 0; g < ng; g++) rejected += ctx->dev[g].h_accum[2];
     if (rejected)
         return set_error(XS_ERR_ARG, "xs_gpu_lookup_samples: %llu sample(s) with a material outside [0, %d) or an energy outside [0, 1]",
                          rejected, XS_NUM_MATERIALS);
-    res->h2d_bytes = (unsigned long long)n * (sizeof(double) + sizeof(int));
-    if (h_macro_xs_out) res->d2h_bytes += (unsigned long long)n * 5 * sizeof(double);
+    res->h2d_bytes = (unsigned long long)n * (sizeof(double) + sizeof(int)) * (bands ? (unsigned long long)ng : 1ULL);
+    if (h_macro_xs_out) res->d2h_bytes += (unsigned long long)n * 5 * sizeof(double) * (bands ? (unsigned long long)ng : 1ULL);
     return XS_OK;
 }
 
@@ -1391,8 +1449,9 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
 {
     DeviceGuard restore_device;
     if (!ctx || n < 0 || first_id < 0) return set_error(XS_ERR_ARG, "xs_gpu_dump: bad argument");
-    if (ctx->n_bands > 1) return set_error(XS_ERR_UNSUPP, "xs_gpu_dump: not available on an energy-band-sharded grid");
     if (n == 0) return XS_OK;
+    // (an energy-band-sharded grid: GPU 0 performs the lookups of ITS band; energies and materials are
+    // complete, macro_xs / argmax of the other bands' lookups read 0 / -1)
     DeviceState &d = ctx->dev[0];
     CUDA_TRY(cudaSetDevice(d.device));
     double *d_e = nullptr, *d_macro = nullptr;
@@ -1405,6 +1464,13 @@ int xs_gpu_dump(xs_gpu_ctx *ctx, long first_id, long n, double *h_energy_out, in
     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
     xs::BatchSource src{};
     src.first_id = first_id; src.count = n; src.mat_lo = 0; src.mat_hi = XS_NUM_MATERIALS - 1;
+    if (ctx->n_bands > 1) {
+        if (!ctx->tile) { cudaFree(d_e); cudaFree(d_macro); cudaFree(d_mat); cudaFree(d_am);
+                          return set_error(XS_ERR_UNSUPP, "xs_gpu_dump: an energy-band-sharded grid needs the tile kernel (XSB200_TILE=1)"); }
+        src.row_begin = (uint32_t)d.row0; src.row_end = (uint32_t)d.row1;
+        CUDA_TRY(cudaMemsetAsync(d_macro, 0, (size_t)n * 5 * sizeof(double), d.stream));
+        CUDA_TRY(cudaMemsetAsync(d_am, 0xff, (size_t)n * sizeof(int), d.stream));
+    }
     xs::BatchSink sink{};
     sink.accum = d.accum; sink.macro_out = d_macro; sink.energy_out = d_e; sink.mat_out = d_mat; sink.argmax_out = d_am;
     int rc = launch_event(ctx, d, src, sink, 0);

@@ -57,6 +57,8 @@ struct BatchSource {
     long   first_id;           // in-kernel sampling: id of slot 0
     long   count;              // number of slots
     int    mat_lo, mat_hi;     // only lookups with mat in [mat_lo, mat_hi] are performed
+    uint32_t row_begin, row_end; // energy-band sharding: only lookups whose unionized row lies in [row_begin, row_end)
+                                 // are performed (row_end == 0: no filter)
 };
 
 struct BatchSink {
@@ -1248,7 +1250,8 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
 __global__ void __launch_bounds__(256)
 xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long n_particles, int lookups,
                        int generation, uint64_t *seeds, const unsigned char *fwd, double *energy, int *mat,
-                       uint32_t *where, unsigned int *mat_histogram)
+                       uint32_t *where, unsigned int *mat_histogram, uint32_t *key, double2 *pack,
+                       uint32_t row_begin, uint32_t row_end)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -1269,8 +1272,13 @@ xs_history_step_kernel(const Problem P, int grid_type, long first_particle, long
         seeds[t] = s;
         energy[t] = e;
         mat[t] = m;
-        where[t] = (uint32_t)locate_rt(P, grid_type, e);
-        atomicAdd(&s_hist[m], 1u);
+        const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
+        where[t] = w;
+        const bool mine = w >= row_begin && w < row_end;      // (energy-band sharding, like the event sampler)
+        if (pack) pack[t] = make_double2(e, __longlong_as_double((long long)w));
+        // the sorted pipeline's key: material, then 28 bits monotone in the energy (like xs_locate_kernel)
+        if (key) key[t] = ((mine ? (uint32_t)m : 15u) << 28) | (uint32_t)fmin(e * 268435456.0, 268435455.0);
+        if (mine) atomicAdd(&s_hist[m], 1u);
     }
     __syncthreads();
     if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
@@ -1291,7 +1299,8 @@ XS_DEV bool sanitize_sample(double &e, int &m)
 
 __global__ void __launch_bounds__(256)
 xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int *mat,
-                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, double2 *pack, unsigned long long *bad)
+                 uint32_t *where, uint32_t *key, unsigned int *mat_histogram, double2 *pack, unsigned long long *bad,
+                 uint32_t row_begin, uint32_t row_end)
 {
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
@@ -1308,11 +1317,14 @@ xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int
         const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
         where[t] = w;
         if (pack) pack[t] = make_double2(e, __longlong_as_double((long long)w));
+        // energy-band sharding: a lookup whose row another device holds gets material 15 in the key (sorted
+        // behind the last segment, never looked up) and is not counted
+        const bool mine = w >= row_begin && w < row_end;
         if (key) {    // same layout as the sampler's key: material, then 28 bits monotone in the energy
             const double scaled = fmin(e * 268435456.0, 268435455.0);
-            key[t] = ((uint32_t)m << 28) | (uint32_t)scaled;
+            key[t] = ((mine ? (uint32_t)m : 15u) << 28) | (uint32_t)scaled;
         }
-        atomicAdd(&s_hist[m], 1u);
+        if (mine) atomicAdd(&s_hist[m], 1u);
     }
     __syncthreads();
     if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])

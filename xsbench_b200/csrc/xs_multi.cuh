@@ -17,7 +17,7 @@ namespace {
 
 typedef struct ncclComm *xs_ncclComm_t;
 typedef int xs_ncclResult_t;                  // ncclSuccess == 0
-enum { XS_NCCL_UINT64 = 5, XS_NCCL_SUM = 0 }; // ncclDataType_t / ncclRedOp_t values (nccl.h)
+enum { XS_NCCL_UINT8 = 1, XS_NCCL_UINT64 = 5, XS_NCCL_SUM = 0 }; // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 struct MultiState {
     void *lib = nullptr;
@@ -78,6 +78,23 @@ int xs_multi_allreduce(xs_gpu_ctx *ctx)
     xs_ncclResult_t r2 = m->GroupEnd();
     if (r == 0) r = r2;
     if (r != 0) return set_error(XS_ERR_NCCL, "ncclAllReduce failed: %s", m->GetErrorString ? m->GetErrorString(r) : "?");
+    return XS_OK;
+}
+
+// History mode on an energy-band-sharded grid: the particles' feedback bytes (n_forward, written by the
+// band that performed the lookup, zero elsewhere) summed over the devices.
+int xs_multi_allreduce_bytes(xs_gpu_ctx *ctx, size_t n_bytes)
+{
+    MultiState *m = static_cast<MultiState *>(ctx->nccl);
+    if (!m || m->n != (int)ctx->dev.size()) return set_error(XS_ERR_NCCL, "NCCL communicators not initialised");
+    xs_ncclResult_t r = m->GroupStart();
+    for (int g = 0; g < m->n && r == 0; g++) {
+        DeviceState &d = ctx->dev[g];
+        r = m->AllReduce(d.hist_fwd, d.hist_fwd, n_bytes, XS_NCCL_UINT8, XS_NCCL_SUM, m->comm[g], d.stream);
+    }
+    xs_ncclResult_t r2 = m->GroupEnd();
+    if (r == 0) r = r2;
+    if (r != 0) return set_error(XS_ERR_NCCL, "ncclAllReduce (history feedback) failed: %s", m->GetErrorString ? m->GetErrorString(r) : "?");
     return XS_OK;
 }
 

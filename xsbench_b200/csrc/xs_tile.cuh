@@ -120,11 +120,12 @@ xs_tile_kernel(const __grid_constant__ Problem P, const BatchSource src, const B
                 }
                 s = apply(hop, s);
                 T.energy[i] = e;
-                T.mat[i] = (signed char)m;
                 if (m >= 0) {
-                    T.where[i] = (uint32_t)locate<GRID>(P, e);
-                    atomicAdd(&T.mat_count[m], 1);
+                    const uint32_t w = (uint32_t)locate<GRID>(P, e);
+                    if (src.row_end && !(w >= src.row_begin && w < src.row_end)) m = -1;     // another device's energy band
+                    else { T.where[i] = w; atomicAdd(&T.mat_count[m], 1); }
                 }
+                T.mat[i] = (signed char)m;
             }
         }
         __syncthreads();
