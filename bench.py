@@ -234,17 +234,23 @@ def gpu_reference_baseline(size: str, lookups: int, device_index: int):
     else:
         env["CUDA_VISIBLE_DEVICES"] = str(device_index)
     for k in (0, 6):
-        try:
-            p = subprocess.run([REF_CUDA, "-m", "event", "-s", size, "-l", str(lookups), "-k", str(k)], env=env,
-                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-            rate = re.search(r"Lookups/s:\s+([\d,]+)", p.stdout)
-            chk = re.search(r"Verification checksum:\s+(\d+)\s+\((\w+)\)", p.stdout)
-            rt = re.search(r"Runtime:\s+([\d.]+) seconds", p.stdout)
-            out[f"k{k}"] = {"lookups_per_s": float(rate.group(1).replace(",", "")) if rate else None,
-                            "runtime_s": float(rt.group(1)) if rt else None,
-                            "checksum": int(chk.group(1)) if chk else None, "valid": bool(chk and chk.group(2) == "Valid")}
-        except Exception as exc:                             # noqa: BLE001 -- a baseline must never take the bench down
-            out[f"k{k}"] = {"error": repr(exc)[:200]}
+        best = None
+        for _ in range(2):      # its timer includes cudaMalloc / Thrust temporaries (a cold first process has read 0.13 s for -k 6): best of two
+            try:
+                p = subprocess.run([REF_CUDA, "-m", "event", "-s", size, "-l", str(lookups), "-k", str(k)], env=env,
+                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+                rate = re.search(r"Lookups/s:\s+([\d,]+)", p.stdout)
+                chk = re.search(r"Verification checksum:\s+(\d+)\s+\((\w+)\)", p.stdout)
+                rt = re.search(r"Runtime:\s+([\d.]+) seconds", p.stdout)
+                one = {"lookups_per_s": float(rate.group(1).replace(",", "")) if rate else None,
+                       "runtime_s": float(rt.group(1)) if rt else None,
+                       "checksum": int(chk.group(1)) if chk else None, "valid": bool(chk and chk.group(2) == "Valid"),
+                       "runs": "best of 2 processes"}
+                if best is None or (one["lookups_per_s"] or 0) > (best.get("lookups_per_s") or 0):
+                    best = one
+            except Exception as exc:                         # noqa: BLE001 -- a baseline must never take the bench down
+                best = best or {"error": repr(exc)[:200]}
+        out[f"k{k}"] = best
     prof = os.path.join(ROOT, "profiles", "r02_reference_cuda_device_times.json")
     if os.path.exists(prof):
         try:

@@ -61,6 +61,12 @@ constexpr int kDenseWarps = kDenseThreads / 32;
 #ifndef XS_DENSE_DEPTH
 #define XS_DENSE_DEPTH 3             // batches in flight ahead of the one being consumed (1 or 3: the ring is a power of two)
 #endif
+#ifndef XS_DENSE_STAGE
+#define XS_DENSE_STAGE 1             // the warp's NEXT group: samples staged in shared memory by cp.async, index rows prefetched
+#endif
+#ifndef XS_DENSE_UNROLL
+#define XS_DENSE_UNROLL 1            // copies of the step body inside a batch (1: see the note at the loop)
+#endif
 #ifndef XS_DENSE_SPAN
 #define XS_DENSE_SPAN 4
 #endif
@@ -70,12 +76,14 @@ constexpr int kDenseWarps = kDenseThreads / 32;
 constexpr int kDensePerLane = XS_DENSE_PER_LANE;       // consecutive lookups per lane
 constexpr int kDenseGroup = 32 * kDensePerLane;        // lookups per warp-group
 constexpr int kDenseBatch = XS_DENSE_BATCH;
+constexpr int kDenseUnroll = XS_DENSE_UNROLL;
 constexpr int kDenseDepth = XS_DENSE_DEPTH;
 constexpr int kDenseRing = kDenseBatch * (kDenseDepth + 1);   // steps of records resident per warp
 constexpr int kDenseSpan = XS_DENSE_SPAN;              // records per ring slot (2..4)
 constexpr int kDenseSlotBytes = kDenseSpan * 128;
 constexpr int kDenseRingBytes = kDenseRing * kDenseSlotBytes;
 constexpr int kDenseFirstWords = 2 * 32 * 2;           // per warp: (first record, record count) per step, double-buffered by chunk
+constexpr int kDenseStageBytes = XS_DENSE_STAGE ? kDenseGroup * 16 : 0;   // per warp: the next group's packed (energy, row) samples
 static_assert(kDenseBatch == 4 && kDenseSpan >= 2 && kDenseSpan <= 4 && (kDenseRing & (kDenseRing - 1)) == 0, "dense kernel geometry");
 
 XS_DEV uint2 lds_v2_u32(uint32_t smem_addr)
@@ -202,7 +210,8 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
     __shared__ unsigned long long s_part[kDenseWarps];
     extern __shared__ __align__(128) uint32_t s_dyn[];       // [record rings][(first record, count) per step][nuclide ids]
     uint32_t *s_first = s_dyn + kDenseWarps * kDenseRingBytes / 4;
-    int *s_nuc = (int *)(s_first + kDenseWarps * kDenseFirstWords);
+    uint32_t *s_stage = s_first + kDenseWarps * kDenseFirstWords;
+    int *s_nuc = (int *)(s_stage + kDenseWarps * kDenseStageBytes / 4);
     __shared__ SegTable T;
     load_seg_table(A, T);
     for (int i = threadIdx.x; i < P.mat_total; i += blockDim.x) s_nuc[i] = P.mat_nuc[i];
@@ -221,6 +230,9 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
     const double2 *my_pairs = opaque(P.pairs + piece_l);
     const uint32_t dst_lane = opaque(ring + (uint32_t)(q_l * kDenseSlotBytes + piece_l * 16));
     const uint32_t desc_lane = opaque(first_base + (uint32_t)(q_l * 8));
+    // this lane's PL entries of the warp's sample staging buffer
+    const uint32_t stage_lane = opaque((uint32_t)__cvta_generic_to_shared(s_stage) + (uint32_t)(warp * kDenseStageBytes + lane * PL * 16));
+    bool staged = false;                                     // the samples of the group about to start are in the staging buffer
 
     int g = warp_next_group(sink, lane);
     while (g < T.n_groups) {
@@ -233,8 +245,21 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
         double e[PL];
         uint32_t where32[PL];
         bool on[PL];
-        // idle slots repeat the group's first lookup: they do not widen the group's energy range
-        load_lane_samples<PL>(A, S, first_in_seg, S.offset + group_first, e, where32, on);
+        if (XS_DENSE_STAGE && staged) {
+            // fetched while the previous group was being worked on (slots past the end of the segment repeat
+            // its last lookup: inside the group's energy range)
+#pragma unroll
+            for (int w = 0; w < PL; w++) {
+                double2 v;
+                asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(stage_lane + w * 16));
+                e[w] = v.x;
+                where32[w] = (uint32_t)__double_as_longlong(v.y);
+                on[w] = first_in_seg + w < S.count;
+            }
+        } else {
+            // idle slots repeat the group's first lookup: they do not widen the group's energy range
+            load_lane_samples<PL>(A, S, first_in_seg, S.offset + group_first, e, where32, on);
+        }
         // The group's energy range.  Energies are non-negative doubles: their bit patterns order
         // like the values (and 64-bit integer compares run on the ALU pipe instead of queueing
         // behind the FP64 work).  The UEG row / hash bin is monotone in the energy, so the
@@ -309,11 +334,13 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
         // the first chunk (two dependent random reads otherwise wait in front of every group).
         uint32_t next_id[PL];
         bool next_any = false;
+        int next_first = 0, next_nuc = 0;                     // the next group's material: nuclide list and length
         if (A.indirect && A.pack) {
             if (g_next < T.n_groups) {
                 const WindowSegment &S2 = T.seg[segment_of_group(T, g_next, sg)];
                 const int first2 = (g_next - S2.group_begin) * kDenseGroup + lane * PL;
                 next_any = true;
+                next_first = S2.first; next_nuc = S2.j_end;
 #pragma unroll
                 for (int w = 0; w < PL; w++)
                     next_id[w] = A.sample_id[S2.offset + min(first2 + w, S2.count - 1)];
@@ -323,6 +350,12 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
         __syncwarp();
         uint32_t multi = resolve(0), multi_next = 0;
         __syncwarp();
+        if (XS_DENSE_STAGE && next_any) {
+            // the next group's samples travel with this group's first batch of records (both come from DRAM:
+            // one latency, not two in a row at the next group's start)
+#pragma unroll
+            for (int w = 0; w < PL; w++) cp_async_16(stage_lane + w * 16, A.pack + next_id[w]);
+        }
 #pragma unroll
         for (int b = 0; b < kDenseDepth; b++) issue(b * kDenseBatch);
 
@@ -338,7 +371,7 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
                     else if (lane >= 30) prefetch_l2(row + lds_s32(nucs + 4u * (uint32_t)min(s + 95, n_nuc - 1)));
                 }
                 if (s + 32 < n_nuc) { multi_next = resolve(s + 32); __syncwarp(); }
-                if ((s == 32 || (s == 0 && n_nuc <= 32)) && next_any) {
+                if (!XS_DENSE_STAGE && (s == 32 || (s == 0 && n_nuc <= 32)) && next_any) {
 #pragma unroll
                     for (int w = 0; w < PL; w++) prefetch_l2(A.pack + next_id[w]);
                 }
@@ -351,8 +384,8 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
             // inlined per-lookup fallbacks ~600) stays resident in the instruction cache; unrolled by the batch
             // it was 3,000 instructions, 20 % of the stall samples were instruction fetches, and the register
             // allocator spilled inside the loop (profiles/r02_notes.md)
-#pragma unroll 1
-            for (int u = 0; u < kDenseBatch; u++, mb >>= 1, slot += kDenseSlotBytes) {
+#pragma unroll kDenseUnroll
+            for (int u = 0; u < kDenseBatch && s + u < n_nuc; u++, mb >>= 1, slot += kDenseSlotBytes) {   // (padded steps of the last batch: skipped)
                 const double conc = C.v[ci + s + u];
                 if (!(mb & 1u)) {
                     // ---- one record for the whole group: straight-line code ----
@@ -429,8 +462,27 @@ xs_dense_kernel(const __grid_constant__ Problem P, const __grid_constant__ Windo
             }
             __syncwarp();                                    // everyone is done with these slots
             issue(s + kDenseDepth * kDenseBatch);
+            if (XS_DENSE_STAGE && GRID == kUnionized && next_any && s + kDenseBatch >= n_steps) {
+                // last batch: the next group's samples have landed -- start its first chunk's two index-row
+                // segments on their way from DRAM (first and last sector of each, like for the chunks after)
+                uint32_t w_min = 0xffffffffu, w_max = 0u;
+#pragma unroll
+                for (int w = 0; w < PL; w++) {
+                    uint32_t row;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(stage_lane + w * 16 + 8));
+                    w_min = min(w_min, row);
+                    w_max = max(w_max, row);
+                }
+                w_min = __reduce_min_sync(kFullMask, w_min);
+                w_max = __reduce_max_sync(kFullMask, w_max);
+                const uint32_t nucs2 = nuc_base + 4u * (uint32_t)next_first;
+                const int *row = P.index_grid + (size_t)((lane & 1) ? w_max : w_min) * (uint32_t)P.n_iso;
+                if (lane < 2)        prefetch_l2(row + lds_s32(nucs2));
+                else if (lane >= 30) prefetch_l2(row + lds_s32(nucs2 + 4u * (uint32_t)(min(32, next_nuc) - 1)));
+            }
         }
         cp_async_wait_group<0>();
+        staged = XS_DENSE_STAGE && next_any;
 
         if (EXACT) finish_lane_lookups<PL>(A, sink, t0, on, acc, my_sum);
         else       finish_lane_lookups_guarded<GRID, PL>(P, A, sink, S.mat, t0, on, e, acc, my_sum);

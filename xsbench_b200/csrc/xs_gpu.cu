@@ -621,7 +621,7 @@ int launch_sorted(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, xs::Ba
         size_t staged = 0;
         const int threads = dense ? xs::kDenseThreads : xs::kBlockThreads, warps = threads / 32;
         if (dense)
-            staged = (size_t)warps * (xs::kDenseRingBytes + xs::kDenseFirstWords * sizeof(uint32_t));
+            staged = (size_t)warps * (xs::kDenseRingBytes + xs::kDenseFirstWords * sizeof(uint32_t) + xs::kDenseStageBytes);
         else if (ctx->grid_type == XS_UNIONIZED)
             staged = (size_t)xs::kWarpsPerBlock * (32 * xs::kLaneWords * sizeof(uint32_t) + xs::kRingBytes);
         const size_t smem = staged + (size_t)d.P.mat_total * sizeof(int);
