@@ -516,6 +516,27 @@ def main():
     e2e_ok = (e2e_verification == res.verification)
     del e_pin, m_pin
 
+    # ---------------- the fused-arithmetic build of the dense kernel (informational) ----------------
+    # XSB200_ARITH=fused is read by xs_gpu_init: a second context (device-generated replica of the same problem)
+    if args.kernel == 6 and not args.no_extras:
+        os.environ["XSB200_ARITH"] = "fused"
+        try:
+            fmats = xs.materials_only(inp)
+            fgpu = xs.move_simulation_data_to_device(cli(6), fmats)
+            fgpu.set_stream(stream.cuda_stream)
+            fin = cli(6)
+            tf, rf = timed_runs(lambda: fgpu.run_range(first_id, n_mine, fin), n_v)
+            f_ops = getattr(fgpu.info(), "fp64_ops_per_pair", 12) or 12
+            variants["k6_fused"] = {"lookups_per_s": total_lookups * n_v / tf, "ms_per_step": 1e3 * tf / n_v,
+                                    "lookup_phase_ms": 1e3 * rf.phase_seconds[2], "fp64_ops_per_pair": f_ops,
+                                    "checksum_matches": bool(rf.verification == res.verification),
+                                    "note": "XSB200_ARITH=fused: 12 FP64 operations per (lookup, nuclide) instead of the reference's 24 roundings; "
+                                            "macro_xs within a few ulp (contract 1e-12), integers guarded; not the default"}
+            fgpu.release()
+            xs.free_simulation_data(fmats)
+        finally:
+            os.environ.pop("XSB200_ARITH", None)
+
     # ---------------- extras: strong scaling of a fixed 10^9 lookups; energy-band sharding ----------------
     strong = bands = None
     if not args.no_extras and args.size == "large":
@@ -659,6 +680,12 @@ def main():
                                               traffic_over_algorithmic=(k0_bytes / alg_step) if k0_bytes else None,
                                               hbm_achieved_frac=(k0_bytes / secs / 1e9 / hbm_peak) if k0_bytes else None,
                                               kernel="xs_tile_kernel<unionized> (one launch: tiles grouped in shared memory, windowed sweep, grid barrier per round)")
+        if "k6_fused" in variants:
+            vf = variants["k6_fused"]
+            f_floor = pairs_mine * vf["fp64_ops_per_pair"] / fp64_peak
+            vf["roofline"] = dict(bound="fp64_issue", floor_ms=1e3 * f_floor, frac=f_floor / (vf["lookup_phase_ms"] * 1e-3),
+                                  note="against its own floor (12 operations); not FP64-bound: shared-memory record delivery and issue slots "
+                                       "bind first (profiles/r02_notes.md)")
         if "k4" in variants and k4_bytes:
             secs = variants["k4"]["lookup_phase_ms"] * 1e-3
             variants["k4"]["roofline"] = dict(bound="l1/l2 gather (see DESIGN.md 5.1b)", traffic=k4_bytes,

@@ -558,7 +558,7 @@ XS_DEV double order_after(double e, double x)
 // slot: a 4-nuclide material needs one round, a 32-nuclide window eight.  A lane keeps its step
 // j in every round; rounds walk over the slots.  All index loads are issued before the first
 // one is consumed.  Steps [jn, n_steps) are padding: record 0 (concentration 0).
-template <int GRID, int ROW_SHIFT>
+template <int GRID, int ROW_SHIFT, bool WIDE = false>
 XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1], const int *nucs, int jn, int n_steps,
                           int slots_on, uint32_t where32, double e, int lane, int j_off = 0)
 {
@@ -575,7 +575,7 @@ XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1]
         double e_s = 0.0;
         if (GRID != kUnionized) e_s = __shfl_sync(kFullMask, e, 4 * s);
         low[r] = 0;
-        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID, GRID == kHash, false>(P, e_s, (long)w_s, nuc);   // hash: probe the records (measured faster); nuclide: the compact grid
+        if (s < slots_on && j < jn) low[r] = nuclide_low<GRID, GRID == kHash, WIDE>(P, e_s, (long)w_s, nuc);   // hash: probe the records (measured faster); nuclide: the compact grid
     }
 #pragma unroll
     for (int r = 0; r < kRounds; r++) {
@@ -589,7 +589,7 @@ XS_DEV void stage_records(const Problem &P, uint32_t (*rec_rows)[kMaxWindow + 1]
 // first concentration in C.v; acc_x / acc_y carry the two channels of lane `quarter` in and out.
 // Shared by xs_window_kernel (lookups grouped in global memory, one window per launch) and
 // xs_tile_kernel (-k 0..3: lookups grouped per tile in shared memory, all windows in one launch).
-template <int GRID>
+template <int GRID, bool WIDE = false>
 XS_DEV void window_sweep_group(const Problem &P, const ConcTable &C, uint32_t (*rec_rows)[kMaxWindow + 1], const int *nucs,
                                int jn, int ci, int slots_on, uint32_t where32, double e, int lane, double &acc_x, double &acc_y)
 {
@@ -600,13 +600,13 @@ XS_DEV void window_sweep_group(const Problem &P, const ConcTable &C, uint32_t (*
     // ---- resolve the record numbers of the window for the 8 lookups of this warp ------
     __syncwarp();
     {
-        if (n_steps <= 4)       stage_records<GRID, 2>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
-        else if (n_steps <= 8)  stage_records<GRID, 3>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
-        else if (n_steps <= 16) stage_records<GRID, 4>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+        if (n_steps <= 4)       stage_records<GRID, 2, WIDE>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+        else if (n_steps <= 8)  stage_records<GRID, 3, WIDE>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+        else if (n_steps <= 16) stage_records<GRID, 4, WIDE>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
         else {
-            stage_records<GRID, 5>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
+            stage_records<GRID, 5, WIDE>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane);
             if (n_steps > 32)   // a folded remainder: steps 32..32 + 2^kFoldShift - 1
-                stage_records<GRID, kFoldShift>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane, 32);
+                stage_records<GRID, kFoldShift, WIDE>(P, rec_rows, nucs, jn, n_steps, slots_on, where32, e, lane, 32);
         }
     }
     __syncwarp();

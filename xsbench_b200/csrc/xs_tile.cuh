@@ -37,6 +37,9 @@ namespace xs {
 #ifndef XS_TILE_LOOKUPS
 #define XS_TILE_LOOKUPS 2048
 #endif
+#ifndef XS_TILE_WIDE
+#define XS_TILE_WIDE 1               // nuclide-grid searches probe their last <= 4 candidates at once (-k 0, 17 M: 371 -> 470 M lookups/s;
+#endif                               // the hash grid's bracket search is better off one probe at a time: 399 vs 336)
 #ifndef XS_TILE_BLOCKS
 #define XS_TILE_BLOCKS 3
 #endif
@@ -170,7 +173,7 @@ xs_tile_kernel(const __grid_constant__ Problem P, const BatchSource src, const B
                             acc_x = part.x;
                             acc_y = part.y;
                         }
-                        window_sweep_group<GRID>(P, C, T.rec[warp], s_nuc + first + j_begin, j_end - j_begin, C.first[m] + j_begin,
+                        window_sweep_group<GRID, XS_TILE_WIDE != 0 && GRID == kNuclide>(P, C, T.rec[warp], s_nuc + first + j_begin, j_end - j_begin, C.first[m] + j_begin,
                                                  min(kSweepSlots, nb - g0), where32, e, lane, acc_x, acc_y);
                         if (!last_window) {
                             if (on && quarter < 3) T.partial[3 * in_batch + quarter] = make_double2(acc_x, acc_y);
