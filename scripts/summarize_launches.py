@@ -15,7 +15,7 @@ for r in rows[1:]:
     d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(',', ''))
 launches = list(d.items())
 names = [k[1] for k, _ in launches]
-STEP = ('xs_sample_kernel', 'sort_', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel', 'xs_dense_kernel')
+STEP = ('xs_sample_kernel', 'sort_', 'xs_build_segments_kernel', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel', 'xs_dense_kernel')
 starts = [i for i, n in enumerate(names) if 'xs_sample_kernel' in n]
 i0 = starts[2]                                   # steps: warm-up, timed 1, timed 2 -> take timed 2
 i1 = i0 + 1
@@ -28,8 +28,8 @@ for (i, n), m in st:
     a = agg.setdefault(short, [0, 0.0, 0.0, 0.0])
     a[0] += 1; a[1] += m['gpu__time_duration.sum']; a[2] += m['dram__bytes_read.sum']; a[3] += m['dram__bytes_write.sum']
 tot = sum(a[1] for a in agg.values())
-L = [f"# {tag} launch list summary: one timed step of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` under ncu", "",
-     f"Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (full list: `{os.path.basename(path)}`).",
+L = [f"# {tag} launch list summary: one timed step of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-traffic-probe --no-extras` under ncu", "",
+     f"Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-traffic-probe --no-extras` (full list: `{os.path.basename(path)}`).",
      f"Times under ncu are cold-cache and serialised: compare shares, not absolutes (un-profiled numbers: `{tag}_bench.json`).", "",
      "| kernel | launches/step | time [us] | share | DRAM read [MB] | DRAM write [MB] |", "|---|---|---|---|---|---|"]
 for k, a in agg.items():

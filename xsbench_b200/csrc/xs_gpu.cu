@@ -152,7 +152,8 @@ struct xs_gpu_ctx {
     int window = 32;                       // nuclides per window (x 1.45 MB of pair records each at n_gp = 11303)
     int tile = 1;                          // -k 0..3 / xs_gpu_dump: xs_tile_kernel (tiles grouped in shared memory, windowed sweep, grid
                                            // barrier per round); 0 = round 1's xs_event_kernel (XSB200_TILE=0)
-    int tile_barrier = 1;                  // XSB200_TILE_BARRIER=0: no grid barrier between rounds (plain launch)
+    int tile_barrier = -1;                 // XSB200_TILE_BARRIER: grid barrier between the rounds of xs_tile_kernel (cooperative launch); -1 = by
+                                           // grid type: measured (-k 0, 17 M, ms with / without) unionized 13.6 / 12.9, hash 41.9 / 59.6, nuclide 35.8 / 44.4
     int device_segments = 1;               // -k 6 / host-sample pipeline: segment tables built on the device, no histogram read-back
     int e2e_split[kMaxChunks] = {};        // XSB200_E2E_SPLIT: chunk sizes of a host-sample call, in percent (0 = built-in schedule)
     int exact_arith = 1;                   // xs_dense_kernel: 1 = the reference's roundings (24 FP64 operations per (lookup, nuclide), macro_xs
@@ -494,7 +495,7 @@ int launch_tile(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs:
     sink.batch_counter = d.counters + counter_slot;           // the round barrier's arrival counter (zeroed per pass)
     const int quantum = 2 * xs::kSweepUnroll;
     int window = std::max(quantum, std::min(ctx->window, 32) / quantum * quantum);
-    int use_barrier = ctx->tile_barrier;
+    int use_barrier = ctx->tile_barrier >= 0 ? ctx->tile_barrier : ctx->grid_type != XS_UNIONIZED;
     if (use_barrier) {
         void *args[] = { (void *)&d.P, (void *)&src, (void *)&sink, (void *)&d.conc, (void *)&window, (void *)&use_barrier };
         CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k, dim3(blocks), dim3(xs::kBlockThreads), args, smem, d.stream));
@@ -1190,7 +1191,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
     ctx->device_segments = env_int("XSB200_DEVICE_SEGMENTS", 1);
     ctx->tile = env_int("XSB200_TILE", 1);
-    ctx->tile_barrier = env_int("XSB200_TILE_BARRIER", 1);
+    ctx->tile_barrier = env_int("XSB200_TILE_BARRIER", -1);
     if (const char *split = getenv("XSB200_E2E_SPLIT")) {
         int n = 0;
         for (const char *p = split; *p && n < kMaxChunks; ) {

@@ -40,6 +40,9 @@ namespace xs {
 #ifndef XS_TILE_WIDE
 #define XS_TILE_WIDE 1               // nuclide-grid searches probe their last <= 4 candidates at once (-k 0, 17 M: 371 -> 470 M lookups/s;
 #endif                               // the hash grid's bracket search is better off one probe at a time: 399 vs 336)
+#ifndef XS_TILE_WINDOW_SYNC
+#define XS_TILE_WINDOW_SYNC 1
+#endif
 #ifndef XS_TILE_BLOCKS
 #define XS_TILE_BLOCKS 3
 #endif
@@ -196,9 +199,11 @@ xs_tile_kernel(const __grid_constant__ Problem P, const BatchSource src, const B
                             if (sink.argmax_out) sink.argmax_out[t] = am;
                         }
                     }
-                    // (multi-window materials: the block moves to the next window together, so its warps --
-                    // and, through the round barrier, the whole grid -- read the same window's records)
-                    if (passes > 1) __syncthreads();
+                    // (multi-window materials: the block moves to the next window together.  Nothing is exchanged
+                    // -- a warp keeps its own groups through all windows -- and with 36 fuel groups over 8 warps
+                    // the barrier makes the warps with 4 groups wait for those with 5 (23 % of the stall samples);
+                    // but without it the warps drift apart and the window falls out of L2: 15.2 instead of 13.6 ms)
+                    if (XS_TILE_WINDOW_SYNC && passes > 1) __syncthreads();
                 }
             }
         }
