@@ -675,11 +675,16 @@ def main():
                         "kernel": "xs_tile_kernel<unionized>" if args.kernel < 4 else "xs_window_kernel<unionized> (all launches of one step)"}
         if "k0" in variants:
             secs = variants["k0"]["lookup_phase_ms"] * 1e-3
-            variants["k0"]["roofline"] = dict(bound="hbm", achieved=alg_step / secs / 1e9, peak=hbm_peak, unit="GB/s",
-                                              frac=alg_step / secs / 1e9 / hbm_peak, traffic=k0_bytes,
-                                              traffic_over_algorithmic=(k0_bytes / alg_step) if k0_bytes else None,
-                                              hbm_achieved_frac=(k0_bytes / secs / 1e9 / hbm_peak) if k0_bytes else None,
-                                              kernel="xs_tile_kernel<unionized> (one launch: tiles grouped in shared memory, windowed sweep, grid barrier per round)")
+            # -k 0 is one launch that keeps a window of pair records L2-resident: DRAM moves a fraction of the
+            # algorithmic bytes, so neither "algorithmic bytes / HBM peak" nor DRAM bandwidth is a fraction of a
+            # roofline that binds; what does is the latency of the L2 gather (ncu: long-scoreboard stalls 47 %,
+            # lts 40 %, l1tex 43 %: profiles/r02_tile_kernel_k0_ncu.txt).  Reported: both HBM views, no `frac`.
+            variants["k0"]["roofline"] = dict(bound="l2 gather latency (window of pair records resident in L2)",
+                                              algorithmic_gbs=alg_step / secs / 1e9, algorithmic_over_hbm_peak=alg_step / secs / 1e9 / hbm_peak,
+                                              traffic=k0_bytes, traffic_over_algorithmic=(k0_bytes / alg_step) if k0_bytes else None,
+                                              hbm_achieved_gbs=(k0_bytes / secs / 1e9) if k0_bytes else None,
+                                              hbm_achieved_frac=(k0_bytes / secs / 1e9 / hbm_peak) if k0_bytes else None, hbm_peak=hbm_peak,
+                                              kernel="xs_tile_kernel<unionized> (one launch: tiles grouped in shared memory, windowed sweep)")
         if "k6_fused" in variants:
             vf = variants["k6_fused"]
             f_floor = pairs_mine * vf["fp64_ops_per_pair"] / fp64_peak

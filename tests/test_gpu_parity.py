@@ -746,3 +746,36 @@ def test_xsbench_binary_write_then_read(tmp_path, grid):
     assert open(tmp_path / "XS_data.dat", "rb").read() == first                         # byte-identical generator
     rc, out = run_xsbench(["-s", "small", "-m", "history", "-G", grid, "-p", "3000", "-b", "read"], cwd=tmp_path)
     assert "Verification checksum:" in out and rc in (0, 1)
+
+
+# ---- the fused-arithmetic build of the dense kernel (XSB200_ARITH=fused, not the default) ---------------------
+@pytest.mark.parametrize("grid,hb", [("unionized", 50), ("hash", 50), ("nuclide", 50)])
+def test_fused_arithmetic_within_contract(monkeypatch, grid, hb):
+    """12 instead of 24 FP64 operations per (lookup, nuclide): macro_xs within the 1e-12 contract (observed: a few
+    ulp), every integer (argmax checksum) bit-exact -- a lookup whose two largest channels are within 1e-10 is
+    recomputed in the reference's order.  Same configuration as test_dense_kernel_at_the_default_split: every
+    material goes through xs_dense_kernel."""
+    monkeypatch.setenv("XSB200_ARITH", "fused")
+    p = Problem("small", 100, grid, hb, method="event", lookups=1_000_000)
+    try:
+        assert p.gpu.info().fp64_ops_per_pair == 12
+        inp = xs.make_inputs(size="small", grid=grid, gridpoints=100, hash_bins=hb, method="event", lookups=1_000_000, kernel_id=6)
+        assert p.gpu.run(inp).verification == p.oracle.event(0, 1_000_000, NTHREADS)
+        rng = np.random.default_rng(19)
+        g = p.oracle.nuclide_grid[0::6]
+        e = np.concatenate([rng.random(300_000), g, np.nextafter(g, 0), np.nextafter(g, 1)])
+        e = e[(e >= 0) & (e < 1)]
+        m = rng.integers(0, 12, len(e)).astype(np.int32)
+        res, macro = p.gpu.lookup_samples(e, m, want_macro_xs=True)
+        v, omacro = p.oracle.lookup_samples(e, m)
+        assert res.verification == v and res.n_lookups == len(e)
+        assert max_rel(macro, omacro) <= REL_TOL
+        assert not np.array_equal(macro, omacro)            # (it really is the other arithmetic)
+    finally:
+        p.close()
+    monkeypatch.delenv("XSB200_ARITH")
+    q = Problem("small", 100, grid, hb, method="event", lookups=1000)
+    try:
+        assert q.gpu.info().fp64_ops_per_pair == 24
+    finally:
+        q.close()
