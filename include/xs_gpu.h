@@ -218,6 +218,20 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
 #define XS_ARRAY_INDEX_GRID        2
 int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_bytes, void *h_dst);
 
+/*
+ * Self-test of the one place where the kernels do NOT use the reference's own operation: the
+ * interpolation factor f = (hi.E - E) / (hi.E - lo.E) is formed from a stored, correctly rounded
+ * reciprocal by one Newton-Markstein step (q = n * inv; r = fma(-d, q, n); f = fma(r, inv, q)) instead of
+ * an IEEE division (cuda/Simulation.cu:168: 14 instructions instead of 4 on this GPU).  The step yields the
+ * correctly rounded quotient whenever q is a faithful approximation, which RN(n * RN(1/d)) is not
+ * guaranteed to be in general; this entry point compares the two on `n_pairs` generated (n, d) pairs and
+ * returns the number of bit mismatches (expected: 0).  mode 0: pairs as the lookups form them (lo < E <= hi
+ * uniform in [0, 1)); mode 1: random mantissas, n <= d, exponents down to 2^-60; mode 2: adversarial
+ * divisors (mantissas of all ones / one bit / near powers of two) against random numerators.
+ */
+int xs_gpu_selftest_division(xs_gpu_ctx *ctx, unsigned long long seed, long n_pairs, int mode,
+                             unsigned long long *mismatches);
+
 /* Use `cuda_stream` (a cudaStream_t) for all work of GPU 0 of this context; NULL = default. */
 int xs_gpu_set_stream(xs_gpu_ctx *ctx, void *cuda_stream);
 

@@ -157,6 +157,18 @@ def test_division_is_exact(small):
     assert np.array_equal(macro, omacro)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_newton_markstein_quotient_equals_ieee_division(small, mode):
+    """The lane-per-lookup kernels form f = (hi.E - E) / d from a stored, correctly rounded 1/d by one Newton-Markstein
+    step and rely on the result being the correctly rounded quotient (macro_xs bit-identical to the reference, no
+    near-tie guard on that path).  Markstein's theorem needs a faithful first approximation, which RN(n * RN(1/d)) is
+    not guaranteed to be in general -- so the claim is tested, not assumed: 2^30 pairs as the lookups form them
+    (lo < E <= hi in [0, 1)), 2^30 with random mantissas and exponents down to 2^-63, 2^28 adversarial divisors."""
+    n = 1 << (28 if mode == 2 else 30)
+    for seed in (1, 0x9e3779b97f4a7c15):
+        assert small.gpu.selftest_division(seed, n, mode) == 0
+
+
 def test_lookups_on_grid_points_only(small):
     """Every lookup energy IS a grid point of one of the first nuclides, in every material: each
     lookup sits exactly ON an interval bound of some nuclide, where "<" and "<=" part ways (and

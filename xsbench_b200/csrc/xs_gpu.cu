@@ -122,6 +122,7 @@ struct DeviceState {
     cudaEvent_t ev[EV_COUNT] = {};
     cudaStream_t copy_stream = nullptr;    // host->device copies of a host-sample call overlap its compute
     cudaEvent_t ev_copy[kMaxChunks] = {}, ev_ready = nullptr;
+    cudaEvent_t ev_chunk[kMaxChunks] = {}; // XSB200_E2E_TRACE=1: end of every chunk's compute (timeline of a host-sample call on stderr)
     int launches = 0;
     // a grouped batch whose histogram read-back has been enqueued but not yet consumed
     struct Pending { bool active = false; int kernel_id = 0; long base = 0, count = 0; const uint32_t *id = nullptr;
@@ -394,7 +395,8 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     CUDA_TRY(cudaMemsetAsync(d.dense_counter, 0, 2 * sizeof(unsigned int), d.stream));
     CUDA_TRY(cudaMalloc(&d.seg_tables, (size_t)kMaxChunks * 2 * sizeof(xs::SegTable)));
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreateWithFlags(&d.ev_copy[i], cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreate(&d.ev_copy[i]));
+    for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreate(&d.ev_chunk[i]));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost(&d.h_accum, 3 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&d.h_hist, 16 * sizeof(unsigned int)));
@@ -498,8 +500,16 @@ int launch_tile(xs_gpu_ctx *ctx, DeviceState &d, const xs::BatchSource &src, xs:
     int use_barrier = ctx->tile_barrier >= 0 ? ctx->tile_barrier : ctx->grid_type != XS_UNIONIZED;
     if (use_barrier) {
         void *args[] = { (void *)&d.P, (void *)&src, (void *)&sink, (void *)&d.conc, (void *)&window, (void *)&use_barrier };
-        CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k, dim3(blocks), dim3(xs::kBlockThreads), args, smem, d.stream));
-    } else {
+        const cudaError_t err = cudaLaunchCooperativeKernel((const void *)k, dim3(blocks), dim3(xs::kBlockThreads), args, smem, d.stream);
+        if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorNotSupported) {
+            // (a device or mode without cooperative launches: same kernel, no barrier -- results do not depend on it)
+            cudaGetLastError();
+            use_barrier = 0;
+        } else {
+            CUDA_TRY(err);
+        }
+    }
+    if (!use_barrier) {
         k<<<blocks, xs::kBlockThreads, smem, d.stream>>>(d.P, src, sink, d.conc, window, use_barrier);
         CUDA_TRY(cudaGetLastError());
     }
@@ -1401,6 +1411,17 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                 else
                     rc = enqueue_grouped_lookup(ctx, d, ctx->e2e_kernel, c_lo, c_n, d.histogram + 16 * c, d.counters + kCursorBase + 16 * c,
                                                 chunk_sink, c == 0);
+                CUDA_TRY(cudaEventRecord(d.ev_chunk[c], d.stream));
+            }
+            if (env_int("XSB200_E2E_TRACE", 0) && rc == XS_OK) {
+                CUDA_TRY(cudaStreamSynchronize(d.stream));
+                for (int c = 0; c < n_chunks; c++) {
+                    float t_copy = 0.f, t_done = 0.f;
+                    cudaEventElapsedTime(&t_copy, d.ev[EV_START], d.ev_copy[c]);
+                    cudaEventElapsedTime(&t_done, d.ev[EV_START], d.ev_chunk[c]);
+                    fprintf(stderr, "[e2e trace] gpu %d chunk %d: %ld samples, copy done %.3f ms, compute done %.3f ms\n", g, c,
+                            bound[c + 1] - bound[c], t_copy, t_done);
+                }
             }
         } else {
             CUDA_TRY(cudaMemcpyAsync(d.samp_e, h_energy + lo, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, d.stream));
@@ -1508,6 +1529,23 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
     return XS_OK;
 }
 
+int xs_gpu_selftest_division(xs_gpu_ctx *ctx, unsigned long long seed, long n_pairs, int mode, unsigned long long *mismatches)
+{
+    DeviceGuard restore_device;
+    if (!ctx || !mismatches || n_pairs < 0 || mode < 0 || mode > 2) return set_error(XS_ERR_ARG, "xs_gpu_selftest_division: bad argument");
+    DeviceState &d = ctx->dev[0];
+    CUDA_TRY(cudaSetDevice(d.device));
+    CUDA_TRY(cudaMemsetAsync(d.accum, 0, 3 * sizeof(unsigned long long), d.stream));
+    if (n_pairs > 0) {
+        xs::xs_division_selftest_kernel<<<d.sm_count * 16, 256, 0, d.stream>>>(seed, n_pairs, mode, d.accum);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(d.h_accum, d.accum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    *mismatches = d.h_accum[0];
+    return XS_OK;
+}
+
 int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_bytes, void *h_dst)
 {
     DeviceGuard restore_device;
@@ -1585,6 +1623,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         if (d.h_hist) cudaFreeHost(d.h_hist);
         for (int i = 0; i < EV_COUNT; i++) if (d.ev[i]) cudaEventDestroy(d.ev[i]);
         for (int i = 0; i < kMaxChunks; i++) if (d.ev_copy[i]) cudaEventDestroy(d.ev_copy[i]);
+        for (int i = 0; i < kMaxChunks; i++) if (d.ev_chunk[i]) cudaEventDestroy(d.ev_chunk[i]);
         if (d.ev_ready) cudaEventDestroy(d.ev_ready);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);

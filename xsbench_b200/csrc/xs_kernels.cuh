@@ -1498,6 +1498,58 @@ xs_history_kernel(const Problem P, long first_particle, long n_particles, int lo
 }
 
 // ---------------------------------------------------------------------------------------
+// Self-test of the Newton-Markstein quotient (xs_gpu_selftest_division): the kernels' f against IEEE division.
+// ---------------------------------------------------------------------------------------
+XS_DEV uint64_t mix64(uint64_t z)          // splitmix64 finaliser: a counter-based generator
+{
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+xs_division_selftest_kernel(unsigned long long seed, long n_pairs, int mode, unsigned long long *mismatches)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    unsigned int bad = 0;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += stride) {
+        const uint64_t a = mix64(seed + 3ULL * (uint64_t)t), b = mix64(seed + 3ULL * (uint64_t)t + 1), c = mix64(seed + 3ULL * (uint64_t)t + 2);
+        double n, d;
+        if (mode == 0) {
+            // as a lookup forms them: grid energies lo < hi and lo < E <= hi, all in [0, 1)
+            const double u1 = (double)(a >> 11) * 0x1p-53, u2 = (double)(b >> 11) * 0x1p-53, u3 = (double)(c >> 11) * 0x1p-53;
+            const double lo = fmin(u1, u2), hi = fmax(u1, u2);
+            double e = lo + u3 * (hi - lo);
+            e = fmin(fmax(e, lo), hi);
+            n = hi - e;
+            d = hi - lo;
+        } else {
+            const int ed = -(int)(b >> 58);                                    // exponent of d in [-63, 0]
+            uint64_t md = a & 0x000fffffffffffffULL;
+            if (mode == 2) {
+                const int k = (int)((c >> 52) & 63) % 52;
+                switch ((int)(c >> 60) & 3) {
+                    case 0: md = 0x000fffffffffffffULL >> (k % 8); break;                     // (nearly) all ones
+                    case 1: md = 1ULL << k; break;                                              // a single bit
+                    case 2: md = 0x000fffffffffffffULL & ~(1ULL << k); break;                   // all ones but one
+                    default: md = (a & 0xffULL) << (k % 44); break;                            // a short pattern somewhere
+                }
+            }
+            d = __longlong_as_double((long long)(((uint64_t)(1023 + ed) << 52) | md));
+            n = d * ((double)(c >> 11) * 0x1p-53);                                              // 0 <= n <= d
+            if (mode == 2 && (c & 1)) n = __longlong_as_double(__double_as_longlong(n) | (long long)(b & 0x7ULL));
+        }
+        if (!(d > 0.0) || !(n >= 0.0) || n > d) continue;
+        const double inv = 1.0 / d;                                                             // IEEE: what xs_build_pairs_kernel stores
+        const double q = n * inv;
+        const double rem = __fma_rn(-d, q, n);
+        const double f = __fma_rn(rem, inv, q);
+        if (__double_as_longlong(f) != __double_as_longlong(n / d)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+// ---------------------------------------------------------------------------------------
 // Bucket table over the unionized grid (built once at init).
 //   bucket[b] = number of rows whose energy maps to a bucket < b
 // ---------------------------------------------------------------------------------------

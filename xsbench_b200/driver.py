@@ -182,6 +182,12 @@ class DeviceSimulation:
         self._check(self._lib.xs_gpu_sort_keys(self._ctx, keys.ctypes.data, keys.shape[0], lo_bit, hi_bit, perm.ctypes.data))
         return perm
 
+    def selftest_division(self, seed: int, n_pairs: int, mode: int = 0) -> int:
+        """Bit mismatches between the kernels' Newton-Markstein quotient and IEEE division over n_pairs generated pairs."""
+        bad = C.c_ulonglong(0)
+        self._check(self._lib.xs_gpu_selftest_division(self._ctx, seed, n_pairs, mode, C.byref(bad)))
+        return int(bad.value)
+
     def read_array(self, which: str) -> np.ndarray:
         """Download one device-resident problem array: 'nuclide_grid' (f64, 6 per point),
         'unionized_energy_array' (f64) or 'index_grid' (i32)."""
