@@ -106,6 +106,7 @@ struct DeviceState {
     unsigned int *bin_chunk_sum = nullptr; // scan scratch
     bool bins_ready = false;               // the event sampler has just counted bin_count for the batch being regrouped
     xs::SortScratch sort{};
+    xs::OnesweepScratch sweep{};           // the one-launch-per-digit sort of the lookup keys
     double2 *pairs = nullptr;              // pair records for the window kernel (128 B per grid point)
     uint32_t *nuc_bucket = nullptr;        // nuclide-grid mode: per-nuclide search tables
     uint32_t *samp_where = nullptr;        // [sample_capacity] UEG row / hash bin per sample
@@ -155,6 +156,7 @@ struct xs_gpu_ctx {
                                            // barrier per round); 0 = round 1's xs_event_kernel (XSB200_TILE=0)
     int tile_barrier = -1;                 // XSB200_TILE_BARRIER: grid barrier between the rounds of xs_tile_kernel (cooperative launch); -1 = by
                                            // grid type: measured (-k 0, 17 M, ms with / without) unionized 13.6 / 12.9, hash 41.9 / 59.6, nuclide 35.8 / 44.4
+    int onesweep = 1;                      // the lookup sort: one launch per digit (XSB200_ONESWEEP=0: round 1's three kernels per pass)
     int device_segments = 1;               // -k 6 / host-sample pipeline: segment tables built on the device, no histogram read-back
     int e2e_split[kMaxChunks] = {};        // XSB200_E2E_SPLIT: chunk sizes of a host-sample call, in percent (0 = built-in schedule)
     int exact_arith = 1;                   // xs_dense_kernel: 1 = the reference's roundings (24 FP64 operations per (lookup, nuclide), macro_xs
@@ -455,6 +457,7 @@ int ensure_sample_buffers(DeviceState &d, long n, bool need_sort, int bin_bits =
         CUDA_TRY(cudaMalloc(&d.hist_seed, cap * sizeof(uint64_t)));
         CUDA_TRY(cudaMalloc(&d.hist_fwd, cap));
         int rc = xs::sort_scratch_alloc(d.sort, d.sample_capacity);
+        if (rc == 0) rc = xs::onesweep_scratch_alloc(d.sweep, d.sample_capacity);
         if (rc != 0) return set_error(XS_ERR_CUDA, "sort scratch allocation failed");
     }
     if (need_sort && bin_bits > 0 && !d.bin_count) {
@@ -695,6 +698,9 @@ int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, int n_m
     return rc;
 }
 
+int sort_lookup_keys(xs_gpu_ctx *ctx, DeviceState &d, uint32_t *key[2], uint32_t *perm[2], long count, int lo_bit, int hi_bit,
+                     uint32_t **sorted_perm, int *launches);
+
 int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bool with_where, bool with_key,
                   bool with_hist)
 {
@@ -751,7 +757,7 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
         // the same order from a stable three-pass radix sort + gather (XSB200_BIN_BITS=0)
         uint32_t *sorted_perm = nullptr;
         uint32_t *key[2] = { d.key[0] + base, d.key[1] + base }, *perm[2] = { d.perm[0] + base, d.perm[1] + base };
-        int rc = xs::sort_lookups(d.sort, key, perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
+        int rc = sort_lookup_keys(ctx, d, key, perm, count, ctx->key_lo_bit, 32, &sorted_perm, &d.launches);
         if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (ctx->sorted_kernel && ctx->fuse_gather) {
             indirect = true;          // the lane-per-lookup kernel applies the permutation itself
@@ -788,6 +794,19 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
     return XS_OK;
 }
 
+// The lookup sort: one launch per digit (xs_sort.cuh, onesweep) or, XSB200_ONESWEEP=0 / very large batches,
+// the three-kernel passes of round 1.  Both are stable and give the same permutation.
+int sort_lookup_keys(xs_gpu_ctx *ctx, DeviceState &d, uint32_t *key[2], uint32_t *perm[2], long count, int lo_bit, int hi_bit,
+                     uint32_t **sorted_perm, int *launches)
+{
+    if (ctx->onesweep) {
+        const int r = xs::onesweep_sort(d.sweep, key, perm, count, lo_bit, hi_bit, d.sm_count, d.stream, sorted_perm, launches);
+        if (r == 0) return 0;
+        if (r != -2) return r;                               // (-2: not applicable -> the three-kernel passes)
+    }
+    return xs::sort_lookups(d.sort, key, perm, count, lo_bit, hi_bit, 0, d.stream, sorted_perm, launches);
+}
+
 // -k 6 without a host round trip: sort, then both lane-per-lookup launches with segment tables a
 // one-thread kernel derives from the histogram.  (The windowed sweep takes its slot ranges as kernel
 // arguments -- measured 5 % faster there -- so -k 4 / 5 keep the read-back.)
@@ -797,7 +816,7 @@ int enqueue_sorted_nosync(xs_gpu_ctx *ctx, DeviceState &d, long base, long count
     CUDA_TRY(cudaSetDevice(d.device));
     uint32_t *sorted_perm = nullptr;
     uint32_t *key[2] = { d.key[0] + base, d.key[1] + base }, *perm[2] = { d.perm[0] + base, d.perm[1] + base };
-    int rc = xs::sort_lookups(d.sort, key, perm, count, ctx->key_lo_bit, 32, 0, d.stream, &sorted_perm, &d.launches);
+    int rc = sort_lookup_keys(ctx, d, key, perm, count, ctx->key_lo_bit, 32, &sorted_perm, &d.launches);
     if (rc != 0) return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
     GroupedBatch b{};
     b.indirect = ctx->fuse_gather != 0;
@@ -1200,6 +1219,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->bin_bits = std::min(20, std::max(0, env_int("XSB200_BIN_BITS", 0)));
     ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
     ctx->device_segments = env_int("XSB200_DEVICE_SEGMENTS", 1);
+    ctx->onesweep = env_int("XSB200_ONESWEEP", 1);
     ctx->tile = env_int("XSB200_TILE", 1);
     ctx->tile_barrier = env_int("XSB200_TILE_BARRIER", -1);
     if (const char *split = getenv("XSB200_E2E_SPLIT")) {
@@ -1522,7 +1542,7 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
     CUDA_TRY(cudaMemcpyAsync(d.key[0], h_keys, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
     uint32_t *sorted_perm = nullptr;
     int launches = 0;
-    if (xs::sort_lookups(d.sort, d.key, d.perm, n, lo_bit, hi_bit, 0, d.stream, &sorted_perm, &launches) != 0)
+    if (sort_lookup_keys(ctx, d, d.key, d.perm, n, lo_bit, hi_bit, &sorted_perm, &launches) != 0)
         return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
     CUDA_TRY(cudaMemcpyAsync(h_perm_out, sorted_perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
@@ -1616,6 +1636,7 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         for (int i = 0; i < 2; i++) { cudaFree(d.key[i]); cudaFree(d.perm[i]); }
         cudaFree(d.bin_count); cudaFree(d.bin_chunk_sum);
         xs::sort_scratch_free(d.sort);
+        xs::onesweep_scratch_free(d.sweep);
         cudaFree(d.samp_where); cudaFree(d.samp_pack); cudaFree(d.grp_e); cudaFree(d.grp_where); cudaFree(d.grp_mat); cudaFree(d.grp_id);
         cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd); cudaFree(d.nuc_bucket);
         cudaFree(d.dump_macro);

@@ -276,6 +276,280 @@ sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// One-launch-per-digit variant for the 32-bit lookup sort ("onesweep": chained scan with decoupled
+// look-back).  One upfront kernel counts the digits of ALL passes (the global digit histogram of a pass does
+// not depend on the order the earlier passes leave); then one kernel per pass: a block takes the next tile
+// by an atomic ticket (tile index = ticket, so every tile it may have to wait for has been started), ranks
+// its keys (the same warp match_any ranking as sort_scatter_kernel), publishes its per-digit counts as an
+// AGGREGATE word, adds up its predecessors' words until it meets an INCLUSIVE one (thread d looks back for
+// digit d, kLookBack predecessors per round trip), publishes its own INCLUSIVE word and scatters.  5 launches
+// per 24-bit sort instead of 12, and the keys are read once per pass instead of twice.
+//
+// Round 1 had tried this with the 2,048-key tiles of the three-kernel scheme (888 tiles resident: the first
+// wave walks hundreds of predecessors, 0.66-1.21 ms against 0.62); the tiles here are 4x-8x larger, so a few
+// hundred are resident and a look-back is a handful of words.
+// A status word = state (2 bits: 0 = nothing yet, 1 = aggregate, 2 = inclusive prefix) | count (30 bits):
+// one 32-bit store publishes both, one 32-bit load reads both.  n < 2^30 keys (larger sorts take the
+// three-kernel path).
+// ---------------------------------------------------------------------------------------
+#ifndef XS_ONESWEEP_ITEMS
+#define XS_ONESWEEP_ITEMS 16
+#endif
+#ifndef XS_ONESWEEP_BLOCKS
+#define XS_ONESWEEP_BLOCKS 3
+#endif
+constexpr int kSweepItems = XS_ONESWEEP_ITEMS;               // keys per thread
+constexpr int kSweepTile = kSortThreads * kSweepItems;      // 4096 keys per block
+constexpr int kLookBack = 8;                                 // predecessors' words in flight per look-back round
+constexpr int kMaxSortPasses = 4;
+
+struct OnesweepScratch {
+    unsigned int *ticket = nullptr;       // [16] next tile of each pass              } one allocation, in this order:
+    unsigned int *digit_hist = nullptr;   // [kMaxSortPasses][kRadix] global digit counts of every pass   } a sort zeroes the
+    unsigned int *status = nullptr;       // [n_passes][n_tiles][kRadix] look-back words                  } prefix it uses
+    long n_tiles_capacity = 0;
+};
+
+inline int onesweep_scratch_alloc(OnesweepScratch &s, long capacity_keys)
+{
+    const long tiles = (capacity_keys + kSweepTile - 1) / kSweepTile;
+    if (tiles <= s.n_tiles_capacity) return 0;
+    cudaFree(s.ticket);
+    s.ticket = nullptr;
+    const size_t words = 16 + (size_t)kMaxSortPasses * kRadix + (size_t)kMaxSortPasses * tiles * kRadix;
+    if (cudaMalloc(&s.ticket, words * sizeof(unsigned int)) != cudaSuccess) return -1;
+    s.digit_hist = s.ticket + 16;
+    s.status = s.digit_hist + kMaxSortPasses * kRadix;
+    s.n_tiles_capacity = tiles;
+    return 0;
+}
+inline void onesweep_scratch_free(OnesweepScratch &s)
+{
+    cudaFree(s.ticket);
+    s = OnesweepScratch{};
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+onesweep_hist_kernel(const uint32_t *__restrict__ keys, long n, int lo_bit, int n_passes, int last_bits, unsigned int *__restrict__ digit_hist)
+{
+    __shared__ unsigned int h[kMaxSortPasses][kRadix];
+    for (int i = threadIdx.x; i < kMaxSortPasses * kRadix; i += kSortThreads) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const long stride = (long)gridDim.x * kSortThreads;
+    for (long i = (long)blockIdx.x * kSortThreads + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < n_passes; p++) {
+            const uint32_t mask = (p == n_passes - 1) ? (1u << last_bits) - 1u : 0xffu;
+            atomicAdd(&h[p][(k >> (lo_bit + 8 * p)) & mask], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_passes * kRadix; i += kSortThreads)
+        if ((&h[0][0])[i]) atomicAdd(digit_hist + i, (&h[0][0])[i]);
+}
+
+// Lanes of the warp holding the same 8-bit digit (valid lanes only).  Eight ballots instead of one
+// match.any: the MATCH instruction is slow on this GPU (every one of the 16 per thread showed up as a
+// short-scoreboard stall, 35 % of the kernel's samples); votes issue at full rate.
+XS_DEV unsigned warp_same_digit(uint32_t d, bool valid)
+{
+    unsigned peers = __ballot_sync(kFullMask, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(kFullMask, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+__global__ void __launch_bounds__(kSortThreads, XS_ONESWEEP_BLOCKS)
+onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, long n, int shift, uint32_t mask,
+                     const unsigned int *__restrict__ digit_hist, unsigned int *status, unsigned int *ticket, int n_tiles)
+{
+    __shared__ unsigned int warp_cnt[kSortWarps][kRadix];
+    __shared__ uint32_t s_key[kSweepTile];
+    __shared__ uint32_t s_val[kSweepTile];
+    __shared__ unsigned int s_gbase[kRadix];                // global position of a digit's run minus its start in the tile
+    __shared__ unsigned int s_warp_tot[kSortWarps];
+    __shared__ unsigned int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (;;) {
+        __syncthreads();                                    // (the previous tile's shared state is no longer read)
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
+        __syncthreads();
+        const int tile = (int)s_tile;
+        if (tile >= n_tiles) break;
+
+        const long base = (long)tile * kSweepTile + (long)warp * (32 * kSweepItems);
+        uint32_t key[kSweepItems];
+        unsigned short rank[kSweepItems];
+#pragma unroll
+        for (int r = 0; r < kSweepItems; r++) {
+            const long idx = base + r * 32 + lane;
+            key[r] = idx < n ? keys_in[idx] : 0u;
+        }
+        // ranking in rounds of 8 items: votes first (independent), then the short serial chain through the
+        // per-warp digit counters
+#pragma unroll
+        for (int r0 = 0; r0 < kSweepItems; r0 += 8) {
+            unsigned peers[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const long idx = base + (r0 + r) * 32 + lane;
+                peers[r] = warp_same_digit((key[r0 + r] >> shift) & mask, idx < n);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const long idx = base + (r0 + r) * 32 + lane;
+                const bool valid = idx < n;
+                const uint32_t d = valid ? (key[r0 + r] >> shift) & mask : (uint32_t)kRadix;
+                const int leader = __ffs(peers[r]) - 1;
+                unsigned int before = 0;
+                if (valid && lane == leader) {
+                    before = warp_cnt[warp][d];
+                    warp_cnt[warp][d] = before + __popc(peers[r]);
+                }
+                before = __shfl_sync(kFullMask, before, leader);
+                rank[r0 + r] = (unsigned short)(before + __popc(peers[r] & lt_mask));
+                __syncwarp();
+            }
+        }
+        // the payloads: all loads in flight now, consumed after the look-back (one at a time inside the scatter
+        // loop they were 29 % of the kernel's stall samples)
+        uint32_t val[kSweepItems];
+#pragma unroll
+        for (int r = 0; r < kSweepItems; r++) {
+            const long idx = base + r * 32 + lane;
+            val[r] = (vals_in && idx < n) ? vals_in[idx] : (uint32_t)idx;
+        }
+        __syncthreads();
+
+        // thread d: this tile's count of digit d -> publish, look back, publish again
+        const int d = threadIdx.x;                          // kSortThreads == kRadix
+        unsigned int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) tot += warp_cnt[w][d];
+        unsigned int *my_status = status + (size_t)tile * kRadix + d;
+        if (tile > 0) {
+            __stcg(my_status, (1u << 30) | tot);            // AGGREGATE
+        }
+        // start of digit d in the whole array = digits below it (exclusive scan of the global histogram)
+        unsigned int below = digit_hist[d];
+        {
+            unsigned int incl = below;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int t = __shfl_up_sync(kFullMask, incl, off);
+                if (lane >= off) incl += t;
+            }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            unsigned int start = incl - below;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; w++) start += w < warp ? s_warp_tot[w] : 0u;
+            below = start;
+            __syncthreads();
+        }
+        unsigned int exclusive = 0;                          // keys of digit d in the tiles before this one
+        int t = tile - 1;
+        while (t >= 0) {
+            unsigned int word[kLookBack];
+#pragma unroll
+            for (int i = 0; i < kLookBack; i++)
+                word[i] = t - i >= 0 ? __ldcg(status + (size_t)(t - i) * kRadix + d) : (2u << 30);
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < kLookBack; i++) {
+                if (done) break;
+                const unsigned int state = word[i] >> 30;
+                if (state == 0) break;                      // not published yet: read again from here
+                exclusive += word[i] & 0x3fffffffu;
+                t--;
+                if (state == 2) done = true;
+            }
+            if (done) break;
+        }
+        __stcg(my_status, (2u << 30) | (exclusive + tot));   // INCLUSIVE
+        // tile-local layout: digit-major, warps in order
+        {
+            unsigned int incl = tot;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int v = __shfl_up_sync(kFullMask, incl, off);
+                if (lane >= off) incl += v;
+            }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            unsigned int start = incl - tot;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; w++) start += w < warp ? s_warp_tot[w] : 0u;
+            s_gbase[d] = below + exclusive - start;
+            unsigned int run = start;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; w++) {
+                const unsigned int c = warp_cnt[w][d];
+                warp_cnt[w][d] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kSweepItems; r++) {
+            const long idx = base + r * 32 + lane;
+            if (idx < n) {
+                const uint32_t dg = (key[r] >> shift) & mask;
+                const unsigned int at = warp_cnt[warp][dg] + rank[r];
+                s_key[at] = key[r];
+                s_val[at] = val[r];
+            }
+        }
+        __syncthreads();
+        const long tile_first = (long)tile * kSweepTile;
+        const int in_tile = (int)((n - tile_first < kSweepTile) ? n - tile_first : kSweepTile);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < in_tile; i += kSortThreads) {
+            const uint32_t k = s_key[i];
+            const unsigned int pos = s_gbase[(k >> shift) & mask] + (unsigned int)i;
+            keys_out[pos] = k;
+            vals_out[pos] = s_val[i];
+        }
+    }
+}
+
+// 32-bit keys, identity payload, bits [lo_bit, hi_bit) in passes of 8 (the last one may be narrower).
+inline int onesweep_sort(OnesweepScratch &s, uint32_t *key[2], uint32_t *perm[2], long n, int lo_bit, int hi_bit,
+                         int sm_count, cudaStream_t stream, uint32_t **sorted_perm, int *launches)
+{
+    const int n_tiles = (int)((n + kSweepTile - 1) / kSweepTile);
+    const int n_passes = (hi_bit - lo_bit + 7) / 8;
+    if (n_tiles == 0) { *sorted_perm = perm[0]; return 0; }
+    if (n_tiles > s.n_tiles_capacity || n_passes > kMaxSortPasses || n >= (1L << 30)) return -2;
+    const size_t used_words = 16 + (size_t)kMaxSortPasses * kRadix + (size_t)n_passes * n_tiles * kRadix;
+    if (cudaMemsetAsync(s.ticket, 0, used_words * sizeof(unsigned int), stream) != cudaSuccess) return -1;
+    const int last_bits = hi_bit - lo_bit - 8 * (n_passes - 1);
+    const int hist_blocks = (int)std::min<long>((n + kSortThreads * 16 - 1) / (kSortThreads * 16), (long)sm_count * 8);
+    onesweep_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(key[0], n, lo_bit, n_passes, last_bits, s.digit_hist);
+    int cur = 0;
+    const int blocks = std::min(n_tiles, sm_count * XS_ONESWEEP_BLOCKS);
+    for (int p = 0; p < n_passes; p++) {
+        const uint32_t mask = (p == n_passes - 1) ? (1u << last_bits) - 1u : 0xffu;
+        onesweep_pass_kernel<<<blocks, kSortThreads, 0, stream>>>(key[cur], p == 0 ? nullptr : perm[cur], key[cur ^ 1], perm[cur ^ 1], n,
+                                                                  lo_bit + 8 * p, mask, s.digit_hist + p * kRadix,
+                                                                  s.status + (size_t)p * n_tiles * kRadix, s.ticket + p, n_tiles);
+        cur ^= 1;
+    }
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    if (launches) *launches += 1 + n_passes;
+    *sorted_perm = perm[cur];
+    return 0;
+}
+
 // Sort bits [lo_bit, hi_bit) of key[0][0..n), 8 bits per pass, stable.  key[]/perm[] are
 // ping-pong buffers; the payload starts as the identity unless `payload_ready` says perm[0]
 // already holds one.  On return *sorted_perm / *sorted_key point at the buffers holding the
