@@ -14,9 +14,10 @@ lookup count}, inside the timed region.
 value : device-timed lookups/s of the whole pipeline [sample -> sort by (material, energy) ->
         lane-per-lookup kernels -> checksum] (-k 6 semantics: like the reference's own fastest
         variant, the sort is inside the timed region); the grid is resident, nothing else is.
-e2e   : the same lookups through the host-buffer C-ABI call xs_gpu_lookup_samples: 12 B/lookup
-        of (energy, material) samples copied from pinned host memory each step, result read
-        back each step.
+e2e   : the same lookups through the host-buffer C-ABI call xs_gpu_lookup_samples: the caller's
+        (f64 energy, int material) samples in pinned host memory -- 12 B/lookup -- are copied each
+        step (9 B/lookup cross PCIe: the library narrows the materials to bytes on the host while
+        the energies are in flight), the result is read back each step.
 roofline: what BINDS the dominant kernel.  For -k 6 that is FP64 issue, not HBM: the sorted
         lookups of a warp share their grid records, so DRAM moves ~3 % of the algorithmic gather
         bytes; the floor is (lookup, nuclide) pairs x FP64 operations per pair / (SMs x 64 FP64
@@ -720,6 +721,10 @@ def main():
                     "device_ms_per_step": 1e3 * statistics.mean(e2e_device_s),
                     "h2d_gbs": h2d / statistics.mean(e2e_device_s) / 1e9 if e2e_device_s else None,
                     "checksum_matches_device_sampled": bool(e2e_ok),
+                    "h2d_bytes_per_lookup": h2d / max(1, n_mine),
+                    "host_side": ("the caller's int materials are narrowed to bytes by host threads inside the call, while the DMA engine "
+                                  "moves the energies (xs_hostpack.h; XSB200_HOST_PACK=0 sends the ints: 12 B/lookup)") if h2d < 12 * n_mine
+                                 else "samples copied as the caller holds them (8 B energy + 4 B material per lookup)",
                     "api": "xs_gpu_lookup_samples (pinned host energy/material samples -> checksum)"},
             "gpu_launches": launches, "clocks": clock_info, "variants": variants,
             "strong": strong, "bands": bands,

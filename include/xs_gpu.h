@@ -232,6 +232,14 @@ int xs_gpu_read_array(xs_gpu_ctx *ctx, int which, long offset_bytes, long n_byte
 int xs_gpu_selftest_division(xs_gpu_ctx *ctx, unsigned long long seed, long n_pairs, int mode,
                              unsigned long long *mismatches);
 
+/*
+ * Host-side helper of xs_gpu_lookup_samples, exposed for tests (needs no GPU and no context): the caller's int
+ * materials narrowed to bytes by `threads` host threads, as they then cross PCIe (17 MB instead of 68 MB per
+ * 17 M samples; a value outside [0, 255] becomes 255, which the device-side validation rejects like any other
+ * material outside [0, 12): the call fails with XS_ERR_ARG).  XSB200_HOST_PACK=0 turns the narrowing off.
+ */
+int xs_gpu_narrow_materials(const int *mat, unsigned char *out, long n, int threads);
+
 /* Use `cuda_stream` (a cudaStream_t) for all work of GPU 0 of this context; NULL = default. */
 int xs_gpu_set_stream(xs_gpu_ctx *ctx, void *cuda_stream);
 

@@ -11,7 +11,7 @@ inp = xs.read_CLI(["-s", "large", "-m", "event", "-G", "unionized", "-l", str(n)
 sd = xs.grid_init_do_not_profile(inp)
 e_pin = m_pin = None
 for cfg in (sys.argv[1:] or [""]):
-    pairs = [kv.split("=") for kv in cfg.split(",") if kv]
+    pairs = [kv.split("=") for kv in cfg.split(",") if "=" in kv]
     for k, v in pairs:
         os.environ[k] = v
     gpu = xs.move_simulation_data_to_device(inp, sd)

@@ -1,11 +1,6 @@
 #!/bin/bash
-# lookups per lane of the dense kernel vs density: -l LOOKUPS sweeps x DENSE_MIN x variants
+# -k 6 phase times against the lookup count (density of the sorted lookups): what a chunk of a host-sample call costs
 set -u
-for L in ${LOOKUPS:-1000000 2000000 4000000 8000000}; do
-  for v in ${VARIANTS:-main pl2 pl1}; do
-    lib=$PWD/xsbench_b200/variants/libxsb200_$v.so
-    [ "$v" = main ] && lib=$PWD/xsbench_b200/libxsb200.so
-    echo "=== lookups $L  $v"
-    XSB200_GPU_LIB=$lib timeout 600 python scripts/quick_bench.py --kernels 6 --reps 3 --lookups $L ${CONFIGS:-"" XSB200_DENSE_MIN=4} 2>&1 | tail -${NCONF:-2}
-  done
+for n in ${NS:-17000000 8500000 5666666 4250000 2125000}; do
+  python scripts/quick_bench.py --kernels 6 --reps ${REPS:-5} --lookups $n ${CONFIGS:-""} 2>&1 | tail -${TAIL:-1} | sed "s/^/n=$n /"
 done

@@ -22,7 +22,7 @@ inp = xs.read_CLI(["-s", a.size, "-m", a.method, "-G", a.grid] + extra)
 sd = xs.grid_init_do_not_profile(inp)
 expected = xs.expected_checksum(inp)
 for cfg in a.configs:
-    pairs = [kv.split("=") for kv in cfg.split(",") if kv]
+    pairs = [kv.split("=") for kv in cfg.split(",") if "=" in kv]
     for k, v in pairs:
         os.environ[k] = v
     gpu = xs.move_simulation_data_to_device(inp, sd)

@@ -83,6 +83,25 @@ def test_argument_errors_do_not_need_a_device():
     xs.free_simulation_data(sd)
 
 
+@pytest.mark.parametrize("n,threads", [(0, 1), (1, 4), (63, 3), (65_535, 8), (65_536, 8), (1_000_003, 1), (1_000_003, 5), (1_000_003, 16)])
+def test_host_side_material_narrowing(n, threads):
+    """xs_gpu_lookup_samples sends the caller's int materials over PCIe as bytes, narrowed by a few host threads
+    (csrc/xs_hostpack.h): every value in [0, 255] survives, anything else becomes 255 (= rejected on the device),
+    whatever the thread count and however ragged the size."""
+    import numpy as np
+    lib = _abi.gpu_lib()
+    rng = np.random.default_rng(n + threads)
+    m = rng.integers(0, 12, n).astype(np.int32)
+    if n > 10:
+        m[rng.integers(0, n, 8)] = np.array([-1, 256, 255, 2**31 - 1, -2**31, 12, 4096 + 3, 65536], dtype=np.int32)
+    out = np.full(n + 64, 0xAA, dtype=np.uint8)
+    assert lib.xs_gpu_narrow_materials(m.ctypes.data, out.ctypes.data, n, threads) == _abi.XS_OK
+    want = np.where((m >= 0) & (m <= 255), m, 255).astype(np.uint8)
+    assert np.array_equal(out[:n], want) and np.all(out[n:] == 0xAA)
+    assert lib.xs_gpu_narrow_materials(m.ctypes.data, out.ctypes.data, -1, threads) == _abi.XS_ERR_ARG
+    assert lib.xs_gpu_narrow_materials(m.ctypes.data, out.ctypes.data, n, 0) == _abi.XS_ERR_ARG
+
+
 @pytest.mark.skipif(_have_gpu(), reason="only meaningful on a machine without a GPU")
 def test_fails_loudly_without_a_gpu():
     inp = xs.make_inputs(size="small", lookups=10, gridpoints=50)

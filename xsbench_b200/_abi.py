@@ -27,7 +27,7 @@ N_PHASES = 4
 #: every symbol include/xs_gpu.h declares
 GPU_SYMBOLS = (
     "xs_gpu_init", "xs_gpu_run", "xs_gpu_run_range", "xs_gpu_lookup_samples", "xs_gpu_dump", "xs_gpu_sort_keys", "xs_gpu_read_array",
-    "xs_gpu_selftest_division", "xs_gpu_set_stream", "xs_gpu_finalize", "xs_gpu_get_info", "xs_gpu_last_error", "xs_gpu_version",
+    "xs_gpu_selftest_division", "xs_gpu_narrow_materials", "xs_gpu_set_stream", "xs_gpu_finalize", "xs_gpu_get_info", "xs_gpu_last_error", "xs_gpu_version",
 )
 #: every symbol host/xs_host.h declares
 HOST_SYMBOLS = (
@@ -159,6 +159,8 @@ def gpu_lib() -> C.CDLL:
     lib.xs_gpu_lookup_samples.argtypes = [ctx_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.POINTER(GpuResult)]
     lib.xs_gpu_dump.restype = C.c_int
     lib.xs_gpu_dump.argtypes = [ctx_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.xs_gpu_narrow_materials.restype = C.c_int
+    lib.xs_gpu_narrow_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int]
     lib.xs_gpu_selftest_division.restype = C.c_int
     lib.xs_gpu_selftest_division.argtypes = [ctx_p, C.c_ulonglong, C.c_long, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.xs_gpu_sort_keys.restype = C.c_int

@@ -24,6 +24,7 @@
 #include "xs_tile.cuh"
 #include "xs_sort.cuh"
 #include "xs_generate.cuh"
+#include "xs_hostpack.h"
 
 namespace {
 
@@ -122,7 +123,10 @@ struct DeviceState {
     long dump_capacity = 0;
     cudaEvent_t ev[EV_COUNT] = {};
     cudaStream_t copy_stream = nullptr;    // host->device copies of a host-sample call overlap its compute
+    uint8_t *h_mat8 = nullptr;             // pinned staging: the caller's materials narrowed to bytes (xs_hostpack.h)
+    long h_mat8_capacity = 0;
     cudaEvent_t ev_copy[kMaxChunks] = {}, ev_ready = nullptr;
+    cudaEvent_t ev_ecopy[kMaxChunks] = {}; // XSB200_E2E_TRACE=1: end of every chunk's energy copy
     cudaEvent_t ev_chunk[kMaxChunks] = {}; // XSB200_E2E_TRACE=1: end of every chunk's compute (timeline of a host-sample call on stderr)
     int launches = 0;
     // a grouped batch whose histogram read-back has been enqueued but not yet consumed
@@ -142,6 +146,9 @@ struct xs_gpu_ctx {
     int blocks_per_sm = 0;                 // 0 = from occupancy
     int sweep = 1;                         // sorted variants use the windowed nuclide sweep kernel
     int e2e_chunks = 0;                    // host-sample pipeline depth (0 = by size)
+    int host_pack = 1;                     // host-sample calls: materials cross PCIe as bytes (XSB200_HOST_PACK=0: as the caller's ints)
+    int pack_threads = 4;                  // ... narrowed by this many host threads (XSB200_PACK_THREADS; the caller's thread is one of them)
+    xs::PackPool *pack_pool = nullptr;
     long max_pass = 1L << 26;              // lookups materialised at once by -k >= 1 (7.5 GB of buffers)
     int bin_bits = 0;                      // -k 6: energy bits of the one-pass bin sort; 0 (default) = three-pass radix sort,
                                            // which measured the same total (5.49 vs 5.56 ms) and keeps a deterministic order
@@ -263,7 +270,11 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     long n_buckets = 0;
     if (ctx->grid_type == XS_UNIONIZED) {
         const long n_ueg = n_points;
-        n_buckets = n_ueg / 2;
+        // one bucket per row on average: the <= 4 rows of a bucket are probed at once, and a warp's 32 lanes
+        // search 32 buckets -- with 2 rows per bucket 83 % of the warps had a lane whose bucket held more than 4
+        // and took a dependent binary-search step first, now 11 % (sampler 0.22 -> 0.20 ms; a table with the
+        // bucket's energies inline was slower: 64 MB of cold sectors per step, profiles/r02_notes.md)
+        n_buckets = n_ueg;
         if (n_buckets < 1) n_buckets = 1;
         if (n_buckets > (1L << 24)) n_buckets = 1L << 24;
         n_buckets = env_int("XSB200_BUCKETS", (int)n_buckets);
@@ -399,6 +410,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     CUDA_TRY(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreate(&d.ev_copy[i]));
     for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreate(&d.ev_chunk[i]));
+    for (int i = 0; i < kMaxChunks; i++) CUDA_TRY(cudaEventCreate(&d.ev_ecopy[i]));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ready, cudaEventDisableTiming));
     CUDA_TRY(cudaMallocHost(&d.h_accum, 3 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMallocHost(&d.h_hist, 16 * sizeof(unsigned int)));
@@ -1211,6 +1223,16 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->sweep = env_int("XSB200_SWEEP", 1);
     ctx->max_pass = std::max(1024, env_int("XSB200_MAX_PASS", 1 << 26));
     ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
+    ctx->host_pack = env_int("XSB200_HOST_PACK", 1);
+    {
+        // host threads that narrow the materials of a host-sample call: a share of the cores per visible GPU
+        // (one process per GPU: the ranks of a node share the host), between 2 and 8
+        int visible = 1;
+        if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) visible = 1;
+        const int cores = (int)std::thread::hardware_concurrency();
+        const int dflt = std::min(8, std::max(2, cores / (2 * visible)));
+        ctx->pack_threads = std::min(64, std::max(1, env_int("XSB200_PACK_THREADS", dflt)));
+    }
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
     ctx->e2e_kernel = env_int("XSB200_E2E_KERNEL", 6) == 4 ? 4 : 6;
@@ -1360,9 +1382,11 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
         return set_error(XS_ERR_UNSUPP, "xs_gpu_lookup_samples: an energy-band-sharded grid needs the sorted pipeline (default knobs)");
     const double t0 = wall_seconds();
     const int ng = (int)ctx->dev.size();
+    unsigned long long mat_bytes_moved = 0;                  // what the materials cost on PCIe: 4 bytes each, or 1 narrowed (xs_hostpack.h)
     for (int g = 0; g < ng; g++) {
         DeviceState &d = ctx->dev[g];
         const long lo = bands ? 0 : n * g / ng, cnt = bands ? n : n * (g + 1) / ng - lo;
+        mat_bytes_moved += (unsigned long long)cnt * sizeof(int);
         const uint32_t band_lo = bands ? (uint32_t)d.row0 : 0u, band_hi = bands ? (uint32_t)d.row1 : 0xffffffffu;
         int rc = ensure_sample_buffers(d, cnt, ctx->sweep != 0);
         if (rc == XS_OK && h_macro_xs_out) rc = ensure_dump_buffer(d, cnt);
@@ -1400,24 +1424,57 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
             {
                 long total_w = 0, run = 0;
                 for (int c = 0; c < n_chunks; c++) total_w += weights[c];
-                for (int c = 0; c < n_chunks; c++) { run += weights[c]; bound[c + 1] = c + 1 == n_chunks ? cnt : cnt * run / total_w; }
+                for (int c = 0; c < n_chunks; c++) { run += weights[c]; bound[c + 1] = c + 1 == n_chunks ? cnt : (cnt * run / total_w) & ~4095L; }    // (copies start on 4 KB boundaries, also as bytes)
             }
             const bool nosync = ctx->e2e_kernel == 6 && ctx->sorted_kernel && ctx->device_segments;
+            // Materials as bytes (xs_hostpack.h): only where nothing downstream reads them as ints -- the sorted
+            // pipeline on packed samples, whose key carries the material.
+            const bool pack_mats = ctx->host_pack && nosync && ctx->pack_samples && ctx->fuse_gather;
+            if (pack_mats) {
+                mat_bytes_moved -= (unsigned long long)cnt * (sizeof(int) - 1);
+                if (cnt > d.h_mat8_capacity) {
+                    if (d.h_mat8) cudaFreeHost(d.h_mat8);
+                    d.h_mat8 = nullptr; d.h_mat8_capacity = 0;
+                    CUDA_TRY(cudaHostAlloc(&d.h_mat8, (size_t)cnt, cudaHostAllocDefault));
+                    d.h_mat8_capacity = cnt;
+                }
+                if (!ctx->pack_pool) ctx->pack_pool = new (std::nothrow) xs::PackPool(ctx->pack_threads - 1);
+                if (!ctx->pack_pool) return set_error(XS_ERR_ARG, "out of host memory");
+            }
+            uint8_t *d_mat8 = reinterpret_cast<uint8_t *>(d.samp_mat);       // (the byte view of the same device buffer)
             CUDA_TRY(cudaEventRecord(d.ev_ready, d.stream));
             CUDA_TRY(cudaStreamWaitEvent(d.copy_stream, d.ev_ready, 0));
-            for (int c = 0; c < n_chunks; c++) {
-                const long c_lo = bound[c], c_n = bound[c + 1] - c_lo;
-                CUDA_TRY(cudaMemcpyAsync(d.samp_e + c_lo, h_energy + lo + c_lo, (size_t)c_n * sizeof(double), cudaMemcpyHostToDevice, d.copy_stream));
-                CUDA_TRY(cudaMemcpyAsync(d.samp_mat + c_lo, h_mat + lo + c_lo, (size_t)c_n * sizeof(int), cudaMemcpyHostToDevice, d.copy_stream));
-                CUDA_TRY(cudaEventRecord(d.ev_copy[c], d.copy_stream));
-            }
+            // A chunk's copies (one copy stream), then its kernels.  Narrowed materials: the host narrows chunk c
+            // while the DMA engine moves chunk c's energies, and the next chunk's energies are enqueued before this
+            // chunk's kernels so the engine does not idle meanwhile.  (Tried and slower, profiles/r02_notes.md: the
+            // materials on a stream of their own -- copies run in submission order whatever their stream --, and all
+            // materials narrowed up front in one copy.)
+            auto copy_energies = [&](int c) {
+                cudaError_t e = cudaMemcpyAsync(d.samp_e + bound[c], h_energy + lo + bound[c], (size_t)(bound[c + 1] - bound[c]) * sizeof(double),
+                                                cudaMemcpyHostToDevice, d.copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(d.ev_ecopy[c], d.copy_stream);
+                return e;
+            };
+            double pack_ms[kMaxChunks] = {};                                   // (host timeline, for XSB200_E2E_TRACE)
+            CUDA_TRY(copy_energies(0));
             for (int c = 0; c < n_chunks && rc == XS_OK; c++) {
                 const long c_lo = bound[c], c_n = bound[c + 1] - c_lo;
+                if (pack_mats) {
+                    const double tp = wall_seconds();
+                    ctx->pack_pool->run(h_mat + lo + c_lo, d.h_mat8 + c_lo, c_n);
+                    pack_ms[c] = 1e3 * (wall_seconds() - tp);
+                    CUDA_TRY(cudaMemcpyAsync(d_mat8 + c_lo, d.h_mat8 + c_lo, (size_t)c_n, cudaMemcpyHostToDevice, d.copy_stream));
+                } else {
+                    CUDA_TRY(cudaMemcpyAsync(d.samp_mat + c_lo, h_mat + lo + c_lo, (size_t)c_n * sizeof(int), cudaMemcpyHostToDevice, d.copy_stream));
+                }
+                CUDA_TRY(cudaEventRecord(d.ev_copy[c], d.copy_stream));
+                if (c + 1 < n_chunks) CUDA_TRY(copy_energies(c + 1));
                 CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_copy[c], 0));
                 if (c_n <= 0) continue;
                 const int blocks = (int)std::min<long>((c_n + 255) / 256, (long)d.sm_count * 16);
                 xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
-                                                                 d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
+                                                                 pack_mats ? d_mat8 + c_lo : nullptr,
+                                                                 pack_mats ? nullptr : d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
                                                                  d.histogram + 16 * c,
                                                                  ctx->e2e_kernel == 6 && ctx->pack_samples ? d.samp_pack + c_lo : nullptr,
                                                                  d.accum + 2, band_lo, band_hi);
@@ -1436,11 +1493,13 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
             if (env_int("XSB200_E2E_TRACE", 0) && rc == XS_OK) {
                 CUDA_TRY(cudaStreamSynchronize(d.stream));
                 for (int c = 0; c < n_chunks; c++) {
-                    float t_copy = 0.f, t_done = 0.f;
+                    float t_copy = 0.f, t_done = 0.f, t_e = 0.f;
+                    cudaEventElapsedTime(&t_e, d.ev[EV_START], d.ev_ecopy[c]);
+                    fprintf(stderr, "[e2e trace] energies of chunk %d in at %.3f ms\n", c, t_e);
                     cudaEventElapsedTime(&t_copy, d.ev[EV_START], d.ev_copy[c]);
                     cudaEventElapsedTime(&t_done, d.ev[EV_START], d.ev_chunk[c]);
-                    fprintf(stderr, "[e2e trace] gpu %d chunk %d: %ld samples, copy done %.3f ms, compute done %.3f ms\n", g, c,
-                            bound[c + 1] - bound[c], t_copy, t_done);
+                    fprintf(stderr, "[e2e trace] gpu %d chunk %d: %ld samples, copy done %.3f ms, compute done %.3f ms; host: materials narrowed in %.3f ms "
+                            "(%d threads)\n", g, c, bound[c + 1] - bound[c], t_copy, t_done, pack_ms[c], pack_mats ? ctx->pack_threads : 0);
                 }
             }
         } else {
@@ -1481,7 +1540,7 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
     if (rejected)
         return set_error(XS_ERR_ARG, "xs_gpu_lookup_samples: %llu sample(s) with a material outside [0, %d) or an energy outside [0, 1]",
                          rejected, XS_NUM_MATERIALS);
-    res->h2d_bytes = (unsigned long long)n * (sizeof(double) + sizeof(int)) * (bands ? (unsigned long long)ng : 1ULL);
+    res->h2d_bytes = (unsigned long long)n * sizeof(double) * (bands ? (unsigned long long)ng : 1ULL) + mat_bytes_moved;
     if (h_macro_xs_out) res->d2h_bytes += (unsigned long long)n * 5 * sizeof(double) * (bands ? (unsigned long long)ng : 1ULL);
     return XS_OK;
 }
@@ -1546,6 +1605,15 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
         return set_error(XS_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(cudaGetLastError()));
     CUDA_TRY(cudaMemcpyAsync(h_perm_out, sorted_perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(cudaStreamSynchronize(d.stream));
+    return XS_OK;
+}
+
+int xs_gpu_narrow_materials(const int *mat, unsigned char *out, long n, int threads)
+{
+    if (n < 0 || threads < 1 || threads > 64 || (n > 0 && (!mat || !out)))
+        return set_error(XS_ERR_ARG, "xs_gpu_narrow_materials: bad argument");
+    xs::PackPool pool(threads - 1);
+    pool.run(mat, out, n);
     return XS_OK;
 }
 
@@ -1625,6 +1693,8 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
     DeviceGuard restore_device;
     if (!ctx) return XS_OK;
     xs_multi_destroy(ctx);
+    delete ctx->pack_pool;
+    ctx->pack_pool = nullptr;
     for (DeviceState &d : ctx->dev) {
         if (d.device < 0) continue;
         cudaSetDevice(d.device);
@@ -1641,10 +1711,12 @@ int xs_gpu_finalize(xs_gpu_ctx *ctx)
         cudaFree(d.sweep_partial); cudaFree(d.pairs); cudaFree(d.hist_seed); cudaFree(d.hist_fwd); cudaFree(d.nuc_bucket);
         cudaFree(d.dump_macro);
         if (d.h_accum) cudaFreeHost(d.h_accum);
+        if (d.h_mat8) cudaFreeHost(d.h_mat8);
         if (d.h_hist) cudaFreeHost(d.h_hist);
         for (int i = 0; i < EV_COUNT; i++) if (d.ev[i]) cudaEventDestroy(d.ev[i]);
         for (int i = 0; i < kMaxChunks; i++) if (d.ev_copy[i]) cudaEventDestroy(d.ev_copy[i]);
         for (int i = 0; i < kMaxChunks; i++) if (d.ev_chunk[i]) cudaEventDestroy(d.ev_chunk[i]);
+        for (int i = 0; i < kMaxChunks; i++) if (d.ev_ecopy[i]) cudaEventDestroy(d.ev_ecopy[i]);
         if (d.ev_ready) cudaEventDestroy(d.ev_ready);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.own_stream && d.stream) cudaStreamDestroy(d.stream);

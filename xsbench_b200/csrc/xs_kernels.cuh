@@ -481,6 +481,8 @@ struct MatShape { int first[kNumMaterials + 1]; int n_nuc[kNumMaterials]; };
 // Device-side replacement of the host loop in launch_sorted: which materials are dense (>= dense_min lookups
 // per grid interval), their slot ranges in the sorted batch (prefix of the histogram: the sort key's top
 // bits are the material) and their warp-groups.  One thread; 12 materials.
+// (Narrower warp-groups for materials under the threshold -- 1 or 2 lookups per lane, so that a group again spans
+// few records -- were measured in round 2 and lost to xs_sorted_kernel at every size: profiles/r02_notes.md.)
 __global__ void xs_build_segments_kernel(const unsigned int *hist, MatShape shape, long dense_threshold, int dense_group,
                                          int sparse_group, SegTable *dense, SegTable *sparse)
 {
@@ -1298,24 +1300,25 @@ XS_DEV bool sanitize_sample(double &e, int &m)
 }
 
 __global__ void __launch_bounds__(256)
-xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int *mat,
+xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int *mat, uint8_t *mat8,
                  uint32_t *where, uint32_t *key, unsigned int *mat_histogram, double2 *pack, unsigned long long *bad,
                  uint32_t row_begin, uint32_t row_end)
 {
+    // materials: ints as the caller holds them, or (mat8) the bytes the host narrowed them to (xs_hostpack.h)
     __shared__ unsigned int s_hist[kNumMaterials];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
         double e = energy[t];
-        int m = mat[t];
+        int m = mat8 ? (int)mat8[t] : mat[t];
         if (!sanitize_sample(e, m)) {
             atomicAdd(bad, 1ULL);
             energy[t] = e;
-            mat[t] = m;
+            if (mat8) mat8[t] = (uint8_t)m; else mat[t] = m;
         }
         const uint32_t w = (uint32_t)locate_rt(P, grid_type, e);
-        where[t] = w;
+        if (where) where[t] = w;
         if (pack) pack[t] = make_double2(e, __longlong_as_double((long long)w));
         // energy-band sharding: a lookup whose row another device holds gets material 15 in the key (sorted
         // behind the last segment, never looked up) and is not counted
