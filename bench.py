@@ -515,6 +515,28 @@ def main():
     barrier()
     e2e_s = max_over_ranks([time.perf_counter() - t0])[0]    # host wall clock: includes the copies and the sync
     e2e_ok = (e2e_verification == res.verification)
+    # the copy alone, all ranks at once: what PCIe / the host's memory system allow this many GPUs of the node to
+    # pull at the same time (the ceiling of the e2e number: at N = 8 the ranks share the host's root complexes)
+    copy_floor = None
+    try:
+        d_e = torch.empty(n_mine, dtype=torch.float64, device="cuda")
+        d_m = torch.empty(n_mine, dtype=torch.int32, device="cuda")
+        best = None
+        for _ in range(3):
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            d_e.copy_(e_pin, non_blocking=True)
+            d_m.copy_(m_pin, non_blocking=True)
+            c1.record()
+            c1.synchronize()
+            ms = max_over_ranks([c0.elapsed_time(c1)])[0]
+            best = ms if best is None else min(best, ms)
+        copy_floor = {"ms_12B_per_lookup": best, "gbs_per_gpu": 12 * n_mine / best / 1e6,
+                      "what": "cudaMemcpyAsync of the same pinned (f64 energy, int material) arrays on all ranks at once, nothing else running: best of 3, max over ranks"}
+        del d_e, d_m
+    except Exception as exc:                                  # informational only
+        copy_floor = {"error": str(exc)[:200]}
     del e_pin, m_pin
 
     # ---------------- the fused-arithmetic build of the dense kernel (informational) ----------------
@@ -721,7 +743,7 @@ def main():
                     "device_ms_per_step": 1e3 * statistics.mean(e2e_device_s),
                     "h2d_gbs": h2d / statistics.mean(e2e_device_s) / 1e9 if e2e_device_s else None,
                     "checksum_matches_device_sampled": bool(e2e_ok),
-                    "h2d_bytes_per_lookup": h2d / max(1, n_mine),
+                    "h2d_bytes_per_lookup": h2d / max(1, n_mine), "copy_only": copy_floor,
                     "host_side": ("the caller's int materials are narrowed to bytes by host threads inside the call, while the DMA engine "
                                   "moves the energies (xs_hostpack.h; XSB200_HOST_PACK=0 sends the ints: 12 B/lookup)") if h2d < 12 * n_mine
                                  else "samples copied as the caller holds them (8 B energy + 4 B material per lookup)",
