@@ -793,3 +793,11 @@ def test_fused_arithmetic_within_contract(monkeypatch, grid, hb):
         assert q.gpu.info().fp64_ops_per_pair == 24
     finally:
         q.close()
+
+
+# ---- the driver's smoke() entry point itself -----------------------------------------------------------------------
+def test_graft_entry_smoke():
+    """__graft_entry__.smoke() is what the driver runs on the GPU box before the bench: keep it in the suite so a
+    change in the pipeline (launch counts, defaults) cannot break it unnoticed."""
+    import __graft_entry__ as entry
+    entry.smoke()
