@@ -5,12 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import numpy as np
 import xsbench_b200 as xs
 os.environ["XSB200_E2E_CHUNKS"] = "1"
-n = 17_000_000
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 17_000_000
+per_material = len(sys.argv) <= 2
 inp = xs.read_CLI(["-s", "large", "-m", "event", "-G", "unionized", "-l", str(n)])
 sd = xs.grid_init_do_not_profile(inp)
 gpu = xs.move_simulation_data_to_device(inp, sd)
 e, m, _, _ = gpu.dump(0, n)
-for name, sel in (("all", slice(None)), ("fuel", m == 0), ("non-fuel", m != 0)) + tuple((f"mat{k}", m == k) for k in range(1, 12)):
+for name, sel in (("all", slice(None)), ("fuel", m == 0), ("non-fuel", m != 0)) + (tuple((f"mat{k}", m == k) for k in range(1, 12)) if per_material else ()):
     ee, mm = np.ascontiguousarray(e[sel]), np.ascontiguousarray(m[sel])
     best = None
     for _ in range(3):
