@@ -15,7 +15,7 @@ for r in rows[1:]:
     d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(',', ''))
 launches = list(d.items())
 names = [k[1] for k, _ in launches]
-STEP = ('xs_sample_kernel', 'sort_', 'xs_build_segments_kernel', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel', 'xs_dense_kernel')
+STEP = ('xs_sample_kernel', 'sort_', 'onesweep_', 'xs_build_segments_kernel', 'xs_gather_kernel', 'xs_bin_scatter', 'xs_partition_kernel', 'xs_window_kernel', 'xs_sorted_kernel', 'xs_dense_kernel')
 starts = [i for i, n in enumerate(names) if 'xs_sample_kernel' in n]
 i0 = starts[2]                                   # steps: warm-up, timed 1, timed 2 -> take timed 2
 i1 = i0 + 1
