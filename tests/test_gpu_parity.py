@@ -127,7 +127,8 @@ def test_lookup_samples_matches_oracle(small):
     assert res.verification == v and res.n_lookups == len(e)
     assert max_rel(macro, omacro) <= REL_TOL
     # (8 B energy + the material narrowed to 1 byte on the host; XSB200_HOST_PACK=0: the caller's 4-byte int)
-    assert res.h2d_bytes == len(e) * 9 and res.d2h_bytes >= len(e) * 40
+    # (on a host with fewer than 8 hardware threads per visible GPU the narrowing is off by default: 12 B)
+    assert res.h2d_bytes in (len(e) * 9, len(e) * 12) and res.d2h_bytes >= len(e) * 40
 
 
 def test_sweep_path_is_bit_identical_to_reference_order(small):
@@ -300,6 +301,7 @@ def test_gather_variants_agree(monkeypatch):
     {"XSB200_DENSE_MIN": "1", "XSB200_KEY_LO_BIT": "26"},   # dense kernel on a barely sorted batch: nearly every lookup resolves itself
     {"XSB200_DENSE_MIN": "1", "XSB200_FUSE_GATHER": "0"},   # dense kernel on gathered (not indirect) samples
     {"XSB200_HOST_PACK": "0"},          # host-sample API: materials cross PCIe as the caller's ints, not narrowed to bytes
+    {"XSB200_HOST_PACK": "1", "XSB200_PACK_THREADS": "3"},   # ... narrowed by 3 host threads whatever the host looks like
 ])
 @pytest.mark.parametrize("grid,hb", [("unionized", 500), ("hash", 500), ("nuclide", 500)])
 def test_sorted_pipeline_variants_agree(monkeypatch, env, grid, hb):
