@@ -300,6 +300,8 @@ def test_gather_variants_agree(monkeypatch):
     {"XSB200_DENSE_MIN": "20"},         # some materials dense, some not: two launches
     {"XSB200_DENSE_MIN": "1", "XSB200_KEY_LO_BIT": "26"},   # dense kernel on a barely sorted batch: nearly every lookup resolves itself
     {"XSB200_DENSE_MIN": "1", "XSB200_FUSE_GATHER": "0"},   # dense kernel on gathered (not indirect) samples
+    {"XSB200_FUSE_DIGITS": "0"},        # the sort counts its digits in a pass of its own instead of in the sampler / locate kernels
+    {"XSB200_ONESWEEP": "0"},           # round 1's three-kernel radix passes
     {"XSB200_HOST_PACK": "0"},          # host-sample API: materials cross PCIe as the caller's ints, not narrowed to bytes
     {"XSB200_HOST_PACK": "1", "XSB200_PACK_THREADS": "3"},   # ... narrowed by 3 host threads whatever the host looks like
 ])

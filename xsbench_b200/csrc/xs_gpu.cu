@@ -105,6 +105,8 @@ struct DeviceState {
     uint32_t *key[2] = {nullptr, nullptr}, *perm[2] = {nullptr, nullptr};
     unsigned int *bin_count = nullptr;     // [12 << bin_bits] fine (material, energy) bins of the -k 6 bin sort
     unsigned int *bin_chunk_sum = nullptr; // scan scratch
+    long digits_for = -1;                  // > 0: the kernel that wrote key[0][base..] counted the sort's digits for this many keys (consumed by the next sort)
+    long digits_base = -1;
     bool bins_ready = false;               // the event sampler has just counted bin_count for the batch being regrouped
     xs::SortScratch sort{};
     xs::OnesweepScratch sweep{};           // the one-launch-per-digit sort of the lookup keys
@@ -163,6 +165,7 @@ struct xs_gpu_ctx {
                                            // barrier per round); 0 = round 1's xs_event_kernel (XSB200_TILE=0)
     int tile_barrier = -1;                 // XSB200_TILE_BARRIER: grid barrier between the rounds of xs_tile_kernel (cooperative launch); -1 = by
                                            // grid type: measured (-k 0, 17 M, ms with / without) unionized 13.6 / 12.9, hash 41.9 / 59.6, nuclide 35.8 / 44.4
+    int fuse_digits = 1;                   // ... whose digit counts the sampler / locate kernels take while they write the keys (XSB200_FUSE_DIGITS=0: a pass of its own)
     int onesweep = 1;                      // the lookup sort: one launch per digit (XSB200_ONESWEEP=0: round 1's three kernels per pass)
     int device_segments = 1;               // -k 6 / host-sample pipeline: segment tables built on the device, no histogram read-back
     int e2e_split[kMaxChunks] = {};        // XSB200_E2E_SPLIT: chunk sizes of a host-sample call, in percent (0 = built-in schedule)
@@ -713,6 +716,19 @@ int launch_sweep(xs_gpu_ctx *ctx, DeviceState &d, const GroupedBatch &b, int n_m
 int sort_lookup_keys(xs_gpu_ctx *ctx, DeviceState &d, uint32_t *key[2], uint32_t *perm[2], long count, int lo_bit, int hi_bit,
                      uint32_t **sorted_perm, int *launches);
 
+// The kernel about to write `count` sort keys at key[0] + base counts their digits itself (xs_sort.cuh): zero the
+// sort's scratch now, remember for which sort.  XSB200_FUSE_DIGITS=0: the sort reads the keys once more instead.
+xs::DigitSpec begin_digit_count(xs_gpu_ctx *ctx, DeviceState &d, long base, long count)
+{
+    xs::DigitSpec spec;
+    d.digits_for = -1;
+    if (ctx->onesweep && ctx->fuse_digits && count > 0 && xs::onesweep_begin(d.sweep, count, ctx->key_lo_bit, 32, d.stream, &spec)) {
+        d.digits_for = count;
+        d.digits_base = base;
+    }
+    return spec;
+}
+
 int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bool with_where, bool with_key,
                   bool with_hist)
 {
@@ -723,6 +739,7 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
     // -k 6 on the default path reads its samples only as packed (energy, row) records through the
     // sort permutation: the separate arrays are not written then
     const bool pack_only = with_key && ctx->pack_samples && ctx->fuse_gather && ctx->sorted_kernel && !with_bins;
+    const xs::DigitSpec digits = with_key && !with_bins ? begin_digit_count(ctx, d, 0, count) : xs::DigitSpec{};
     xs::xs_sample_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, first_id, count,
                                                        pack_only ? nullptr : d.samp_e, pack_only ? nullptr : d.samp_mat,
                                                        with_where && !pack_only ? d.samp_where : nullptr,
@@ -731,7 +748,7 @@ int launch_sample(xs_gpu_ctx *ctx, DeviceState &d, long first_id, long count, bo
                                                        with_bins ? d.bin_count : nullptr, 28 - ctx->bin_bits,
                                                        ctx->n_bands > 1 ? (uint32_t)d.row0 : 0u,
                                                        ctx->n_bands > 1 ? (uint32_t)d.row1 : 0xffffffffu,
-                                                       with_key && ctx->pack_samples ? d.samp_pack : nullptr);
+                                                       with_key && ctx->pack_samples ? d.samp_pack : nullptr, digits);
     CUDA_TRY(cudaGetLastError());
     d.launches++;
     d.bins_ready = with_bins;
@@ -811,8 +828,11 @@ int enqueue_grouped_front(xs_gpu_ctx *ctx, DeviceState &d, int kernel_id, long b
 int sort_lookup_keys(xs_gpu_ctx *ctx, DeviceState &d, uint32_t *key[2], uint32_t *perm[2], long count, int lo_bit, int hi_bit,
                      uint32_t **sorted_perm, int *launches)
 {
+    // (digits counted by the kernel that wrote exactly these keys, for exactly this sort: see begin_digit_count)
+    const bool counted = d.digits_for == count && key[0] == d.key[0] + d.digits_base && lo_bit == ctx->key_lo_bit && hi_bit == 32;
+    d.digits_for = -1;
     if (ctx->onesweep) {
-        const int r = xs::onesweep_sort(d.sweep, key, perm, count, lo_bit, hi_bit, d.sm_count, d.stream, sorted_perm, launches);
+        const int r = xs::onesweep_sort(d.sweep, key, perm, count, lo_bit, hi_bit, d.sm_count, d.stream, sorted_perm, launches, counted);
         if (r == 0) return 0;
         if (r != -2) return r;                               // (-2: not applicable -> the three-kernel passes)
     }
@@ -1099,6 +1119,7 @@ int enqueue_history_all(xs_gpu_ctx *ctx, long first_particle, long n_particles, 
                     CUDA_TRY(cudaMemsetAsync(d.counters, 0, kNumCounters * sizeof(unsigned int), d.stream));
                     CUDA_TRY(cudaMemsetAsync(d.histogram, 0, kNumHist * sizeof(unsigned int), d.stream));
                     const int blocks = (int)std::min<long>((np + 255) / 256, (long)d.sm_count * 16);
+                    d.digits_for = -1;                        // (this kernel does not count the sort's digits)
                     xs::xs_history_step_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, lo[g] + done, np, lookups, gen,
                                                                            d.hist_seed, d.hist_fwd, d.samp_e, d.samp_mat, d.samp_where,
                                                                            d.histogram, nosync ? d.key[0] : nullptr,
@@ -1245,6 +1266,7 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->dense_min = std::max(0, env_int("XSB200_DENSE_MIN", 64));
     ctx->device_segments = env_int("XSB200_DEVICE_SEGMENTS", 1);
     ctx->onesweep = env_int("XSB200_ONESWEEP", 1);
+    ctx->fuse_digits = env_int("XSB200_FUSE_DIGITS", 1);
     ctx->tile = env_int("XSB200_TILE", 1);
     ctx->tile_barrier = env_int("XSB200_TILE_BARRIER", -1);
     if (const char *split = getenv("XSB200_E2E_SPLIT")) {
@@ -1475,12 +1497,13 @@ int xs_gpu_lookup_samples(xs_gpu_ctx *ctx, const double *h_energy, const int *h_
                 CUDA_TRY(cudaStreamWaitEvent(d.stream, d.ev_copy[c], 0));
                 if (c_n <= 0) continue;
                 const int blocks = (int)std::min<long>((c_n + 255) / 256, (long)d.sm_count * 16);
+                const xs::DigitSpec digits = ctx->e2e_kernel == 6 && nosync ? begin_digit_count(ctx, d, c_lo, c_n) : xs::DigitSpec{};
                 xs::xs_locate_kernel<<<blocks, 256, 0, d.stream>>>(d.P, ctx->grid_type, c_n, d.samp_e + c_lo, d.samp_mat + c_lo,
                                                                  pack_mats ? d_mat8 + c_lo : nullptr,
                                                                  pack_mats ? nullptr : d.samp_where + c_lo, ctx->e2e_kernel == 6 ? d.key[0] + c_lo : nullptr,
                                                                  d.histogram + 16 * c,
                                                                  ctx->e2e_kernel == 6 && ctx->pack_samples ? d.samp_pack + c_lo : nullptr,
-                                                                 d.accum + 2, band_lo, band_hi);
+                                                                 d.accum + 2, band_lo, band_hi, digits);
                 CUDA_TRY(cudaGetLastError());
                 d.launches++;
                 if (c == 0) CUDA_TRY(cudaEventRecord(d.ev[EV_SAMPLED], d.stream));
@@ -1602,6 +1625,7 @@ int xs_gpu_sort_keys(xs_gpu_ctx *ctx, const uint32_t *h_keys, long n, int lo_bit
     if (rc != XS_OK) return rc;
     CUDA_TRY(cudaSetDevice(d.device));
     CUDA_TRY(cudaMemcpyAsync(d.key[0], h_keys, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+    d.digits_for = -1;
     uint32_t *sorted_perm = nullptr;
     int launches = 0;
     if (sort_lookup_keys(ctx, d, d.key, d.perm, n, lo_bit, hi_bit, &sorted_perm, &launches) != 0)

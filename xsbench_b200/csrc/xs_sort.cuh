@@ -516,36 +516,82 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         for (int i = threadIdx.x; i < in_tile; i += kSortThreads) {
             const uint32_t k = s_key[i];
             const unsigned int pos = s_gbase[(k >> shift) & mask] + (unsigned int)i;
-            keys_out[pos] = k;
+            if (keys_out) keys_out[pos] = k;                // (null in the last pass: nothing reads the sorted keys)
             vals_out[pos] = s_val[i];
         }
     }
 }
 
+// What a kernel that WRITES the keys needs to count their digits on the way (the sampler / locate kernels do:
+// the sort then starts without onesweep_hist_kernel's pass over the keys).  digit_hist == nullptr: do not count.
+struct DigitSpec {
+    unsigned int *digit_hist = nullptr;   // [n_passes][kRadix], zeroed by onesweep_begin
+    int lo_bit = 0, n_passes = 0, last_bits = 8;
+};
+
+// Shared-memory side of that: zero, count one key, flush (all threads of the block call zero / flush).
+XS_DEV void digit_count_zero(unsigned int (*h)[kRadix])
+{
+    for (int i = threadIdx.x; i < kMaxSortPasses * kRadix; i += blockDim.x) (&h[0][0])[i] = 0;
+}
+XS_DEV void digit_count_key(unsigned int (*h)[kRadix], const DigitSpec &spec, uint32_t k)
+{
+    for (int p = 0; p < spec.n_passes; p++) {
+        const uint32_t mask = (p == spec.n_passes - 1) ? (1u << spec.last_bits) - 1u : 0xffu;
+        atomicAdd(&h[p][(k >> (spec.lo_bit + 8 * p)) & mask], 1u);
+    }
+}
+XS_DEV void digit_count_flush(unsigned int (*h)[kRadix], const DigitSpec &spec)
+{
+    for (int i = threadIdx.x; i < spec.n_passes * kRadix; i += blockDim.x)
+        if ((&h[0][0])[i]) atomicAdd(spec.digit_hist + i, (&h[0][0])[i]);
+}
+
+// Zero the scratch a sort of n keys over bits [lo_bit, hi_bit) uses and describe its digits.  Returns false when
+// onesweep_sort would not take this sort (the caller's kernel then does not count: spec->digit_hist stays null).
+inline bool onesweep_begin(OnesweepScratch &s, long n, int lo_bit, int hi_bit, cudaStream_t stream, DigitSpec *spec)
+{
+    *spec = DigitSpec{};
+    const int n_tiles = (int)((n + kSweepTile - 1) / kSweepTile);
+    const int n_passes = (hi_bit - lo_bit + 7) / 8;
+    if (n_tiles == 0 || n_tiles > s.n_tiles_capacity || n_passes > kMaxSortPasses || n >= (1L << 30)) return false;
+    const size_t used_words = 16 + (size_t)kMaxSortPasses * kRadix + (size_t)n_passes * n_tiles * kRadix;
+    if (cudaMemsetAsync(s.ticket, 0, used_words * sizeof(unsigned int), stream) != cudaSuccess) return false;
+    spec->digit_hist = s.digit_hist;
+    spec->lo_bit = lo_bit;
+    spec->n_passes = n_passes;
+    spec->last_bits = hi_bit - lo_bit - 8 * (n_passes - 1);
+    return true;
+}
+
 // 32-bit keys, identity payload, bits [lo_bit, hi_bit) in passes of 8 (the last one may be narrower).
+// digits_counted: onesweep_begin ran for exactly this sort and the kernel that wrote the keys counted their digits.
 inline int onesweep_sort(OnesweepScratch &s, uint32_t *key[2], uint32_t *perm[2], long n, int lo_bit, int hi_bit,
-                         int sm_count, cudaStream_t stream, uint32_t **sorted_perm, int *launches)
+                         int sm_count, cudaStream_t stream, uint32_t **sorted_perm, int *launches, bool digits_counted = false)
 {
     const int n_tiles = (int)((n + kSweepTile - 1) / kSweepTile);
     const int n_passes = (hi_bit - lo_bit + 7) / 8;
     if (n_tiles == 0) { *sorted_perm = perm[0]; return 0; }
     if (n_tiles > s.n_tiles_capacity || n_passes > kMaxSortPasses || n >= (1L << 30)) return -2;
-    const size_t used_words = 16 + (size_t)kMaxSortPasses * kRadix + (size_t)n_passes * n_tiles * kRadix;
-    if (cudaMemsetAsync(s.ticket, 0, used_words * sizeof(unsigned int), stream) != cudaSuccess) return -1;
     const int last_bits = hi_bit - lo_bit - 8 * (n_passes - 1);
-    const int hist_blocks = (int)std::min<long>((n + kSortThreads * 16 - 1) / (kSortThreads * 16), (long)sm_count * 8);
-    onesweep_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(key[0], n, lo_bit, n_passes, last_bits, s.digit_hist);
+    if (!digits_counted) {
+        const size_t used_words = 16 + (size_t)kMaxSortPasses * kRadix + (size_t)n_passes * n_tiles * kRadix;
+        if (cudaMemsetAsync(s.ticket, 0, used_words * sizeof(unsigned int), stream) != cudaSuccess) return -1;
+        const int hist_blocks = (int)std::min<long>((n + kSortThreads * 16 - 1) / (kSortThreads * 16), (long)sm_count * 8);
+        onesweep_hist_kernel<<<hist_blocks, kSortThreads, 0, stream>>>(key[0], n, lo_bit, n_passes, last_bits, s.digit_hist);
+        if (launches) *launches += 1;
+    }
     int cur = 0;
     const int blocks = std::min(n_tiles, sm_count * XS_ONESWEEP_BLOCKS);
     for (int p = 0; p < n_passes; p++) {
         const uint32_t mask = (p == n_passes - 1) ? (1u << last_bits) - 1u : 0xffu;
-        onesweep_pass_kernel<<<blocks, kSortThreads, 0, stream>>>(key[cur], p == 0 ? nullptr : perm[cur], key[cur ^ 1], perm[cur ^ 1], n,
+        onesweep_pass_kernel<<<blocks, kSortThreads, 0, stream>>>(key[cur], p == 0 ? nullptr : perm[cur], p == n_passes - 1 ? nullptr : key[cur ^ 1], perm[cur ^ 1], n,
                                                                   lo_bit + 8 * p, mask, s.digit_hist + p * kRadix,
                                                                   s.status + (size_t)p * n_tiles * kRadix, s.ticket + p, n_tiles);
         cur ^= 1;
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    if (launches) *launches += 1 + n_passes;
+    if (launches) *launches += n_passes;
     *sorted_perm = perm[cur];
     return 0;
 }
