@@ -370,8 +370,8 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
                      const unsigned int *__restrict__ digit_hist, unsigned int *status, unsigned int *ticket, int n_tiles)
 {
     __shared__ unsigned int warp_cnt[kSortWarps][kRadix];
-    __shared__ uint32_t s_key[kSweepTile];
-    __shared__ uint32_t s_val[kSweepTile];
+    extern __shared__ uint32_t s_tile_buf[];                // [2][kSweepTile]: the tile's keys and payloads in digit order (dynamic: > 48 KB for tiles beyond 4,096 keys)
+    uint32_t *s_key = s_tile_buf, *s_val = s_tile_buf + kSweepTile;
     __shared__ unsigned int s_gbase[kRadix];                // global position of a digit's run minus its start in the tile
     __shared__ unsigned int s_warp_tot[kSortWarps];
     __shared__ unsigned int s_tile;
@@ -583,9 +583,15 @@ inline int onesweep_sort(OnesweepScratch &s, uint32_t *key[2], uint32_t *perm[2]
     }
     int cur = 0;
     const int blocks = std::min(n_tiles, sm_count * XS_ONESWEEP_BLOCKS);
+    constexpr size_t kTileBytes = 2 * sizeof(uint32_t) * kSweepTile;
+    static bool attr_set = false;                            // (per process; the attribute belongs to the function, not the device state)
+    if (!attr_set) {
+        if (cudaFuncSetAttribute((const void *)onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileBytes) != cudaSuccess) return -1;
+        attr_set = true;
+    }
     for (int p = 0; p < n_passes; p++) {
         const uint32_t mask = (p == n_passes - 1) ? (1u << last_bits) - 1u : 0xffu;
-        onesweep_pass_kernel<<<blocks, kSortThreads, 0, stream>>>(key[cur], p == 0 ? nullptr : perm[cur], p == n_passes - 1 ? nullptr : key[cur ^ 1], perm[cur ^ 1], n,
+        onesweep_pass_kernel<<<blocks, kSortThreads, kTileBytes, stream>>>(key[cur], p == 0 ? nullptr : perm[cur], p == n_passes - 1 ? nullptr : key[cur ^ 1], perm[cur ^ 1], n,
                                                                   lo_bit + 8 * p, mask, s.digit_hist + p * kRadix,
                                                                   s.status + (size_t)p * n_tiles * kRadix, s.ticket + p, n_tiles);
         cur ^= 1;
