@@ -46,6 +46,7 @@ struct Problem {
     long   n_ueg;
     double bucket_scale;         // (double)n_buckets
     int    n_buckets;
+    int    bucket_shift;         // 4: entries are (first row << 4 | min(rows, 15)); 0: plain first rows
     int    nuc_buckets;          // buckets per nuclide (0 = table not built)
     int    n_iso;
     int    n_gp;
@@ -214,8 +215,15 @@ template <bool STREAM>
 XS_DEV long ueg_row_t(const Problem &P, double e)
 {
     const int b = bucket_of(e, P.bucket_scale, P.n_buckets);
-    long lo = STREAM ? ldg_search_u32(P.ueg_bucket + b) : __ldg(P.ueg_bucket + b);   // rows [lo, hi) are in bucket b
-    long hi = STREAM ? ldg_search_u32(P.ueg_bucket + b + 1) : __ldg(P.ueg_bucket + b + 1);
+    // rows [lo, hi) are in bucket b.  A table entry is (first row << 4 | rows in the bucket, 15 = "15 or more"):
+    // one 4-byte read gives both ends, and an empty bucket (37 % of them at one row per bucket) needs no
+    // probe at all -- the sampler kernels are bound by the L1 tag stage, i.e. by sectors requested per lookup
+    // (bucket_shift == 0: plain first-row entries, grids of 2^28 rows and more).
+    const uint32_t ent = STREAM ? ldg_search_u32(P.ueg_bucket + b) : __ldg(P.ueg_bucket + b);
+    long lo = (long)(ent >> P.bucket_shift);
+    const uint32_t cnt = P.bucket_shift ? (ent & 15u) : 15u;
+    long hi = lo + cnt;
+    if (cnt == 15u) hi = (long)((STREAM ? ldg_search_u32(P.ueg_bucket + b + 1) : __ldg(P.ueg_bucket + b + 1)) >> P.bucket_shift);
     // upper_bound within [lo, hi): first row with ueg > e
     while (hi - lo > 4) {
         const long mid = lo + (hi - lo) / 2;

@@ -303,6 +303,7 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
         P.n_ueg = n_ueg;
         P.n_buckets = (int)n_buckets;
         P.bucket_scale = (double)n_buckets;
+        P.bucket_shift = (n_ueg < (1L << 28) && env_int("XSB200_BUCKET_PACK", 1)) ? 4 : 0;
     } else if (ctx->grid_type == XS_HASH) {
         d.hot_bytes = (size_t)in->hash_bins * (size_t)n_iso * sizeof(int);
         CUDA_TRY(cudaMalloc(&d.hot_slab, d.hot_bytes));
@@ -327,8 +328,20 @@ int upload_device(xs_gpu_ctx *ctx, DeviceState &d, const Inputs *in, const Simul
     // kernels index the grid by global row number: bias the pointer by the band's first row
     if (ctx->grid_type == XS_UNIONIZED) P.index_grid = d.index_grid - d.row0 * n_iso;
     if (ctx->grid_type == XS_UNIONIZED) {
-        xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(ueg, n_points, (double)n_buckets, (int)n_buckets, bucket);
-        CUDA_TRY(cudaGetLastError());
+        if (P.bucket_shift) {
+            // first rows into a temporary, then entries with the bucket's row count packed in (xs_pack_buckets_kernel)
+            uint32_t *first = nullptr;
+            CUDA_TRY(cudaMalloc(&first, ((size_t)n_buckets + 1) * sizeof(uint32_t)));
+            xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(ueg, n_points, (double)n_buckets, (int)n_buckets, first);
+            xs::xs_pack_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(first, (int)n_buckets, bucket);
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+            cudaFree(first);
+            CUDA_TRY(e);
+        } else {
+            xs::xs_build_buckets_kernel<<<d.sm_count * 8, 256, 0, d.stream>>>(ueg, n_points, (double)n_buckets, (int)n_buckets, bucket);
+            CUDA_TRY(cudaGetLastError());
+        }
     }
     if (ctx->grid_type == XS_NUCLIDE && env_int("XSB200_NUCLIDE_BUCKETS", 1)) {
         // nuclide-grid mode: a bucket table per nuclide replaces the top ~12 of the 14 (large)

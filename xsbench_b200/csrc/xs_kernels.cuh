@@ -1580,4 +1580,15 @@ __global__ void xs_build_buckets_kernel(const double *ueg, long n_ueg, double sc
     }
 }
 
+// entry[b] = first[b] << 4 | min(first[b + 1] - first[b], 15)   (see ueg_row_t)
+__global__ void xs_pack_buckets_kernel(const uint32_t *first, int n_buckets, uint32_t *entry)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += stride) {
+        const uint32_t f = first[b];
+        const uint32_t rows = b < n_buckets ? first[b + 1] - f : 0u;
+        entry[b] = (f << 4) | (rows < 15u ? rows : 15u);
+    }
+}
+
 }  // namespace xs
