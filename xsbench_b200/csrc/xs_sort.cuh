@@ -584,11 +584,9 @@ inline int onesweep_sort(OnesweepScratch &s, uint32_t *key[2], uint32_t *perm[2]
     int cur = 0;
     const int blocks = std::min(n_tiles, sm_count * XS_ONESWEEP_BLOCKS);
     constexpr size_t kTileBytes = 2 * sizeof(uint32_t) * kSweepTile;
-    static bool attr_set = false;                            // (per process; the attribute belongs to the function, not the device state)
-    if (!attr_set) {
-        if (cudaFuncSetAttribute((const void *)onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileBytes) != cudaSuccess) return -1;
-        attr_set = true;
-    }
+    if (kTileBytes > 48 * 1024 &&                            // (per device: set on whichever device is current)
+        cudaFuncSetAttribute((const void *)onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileBytes) != cudaSuccess)
+        return -1;
     for (int p = 0; p < n_passes; p++) {
         const uint32_t mask = (p == n_passes - 1) ? (1u << last_bits) - 1u : 0xffu;
         onesweep_pass_kernel<<<blocks, kSortThreads, kTileBytes, stream>>>(key[cur], p == 0 ? nullptr : perm[cur], p == n_passes - 1 ? nullptr : key[cur ^ 1], perm[cur ^ 1], n,
