@@ -237,8 +237,9 @@ int xs_gpu_selftest_division(xs_gpu_ctx *ctx, unsigned long long seed, long n_pa
  * materials narrowed to bytes by `threads` host threads, as they then cross PCIe (17 MB instead of 68 MB per
  * 17 M samples; a value outside [0, 255] becomes 255, which the device-side validation rejects like any other
  * material outside [0, 12): the call fails with XS_ERR_ARG).  XSB200_HOST_PACK=0 turns the narrowing off, =1 forces
- * it; by default it is on when the host has at least 8 hardware threads per visible GPU (with less, the narrowing is
- * slower than the copy it shortens and the ints travel as they are).
+ * it; by default it is on when this process has at least 16 hardware threads per GPU to itself (processes sharing the
+ * host are counted from LOCAL_WORLD_SIZE and its MPI / Slurm counterparts); with less, the narrowing is slower than the
+ * copy it shortens and the ints travel as they are.
  */
 int xs_gpu_narrow_materials(const int *mat, unsigned char *out, long n, int threads);
 

@@ -1258,17 +1258,21 @@ int xs_gpu_init(const Inputs *in, const SimulationData *sd, int n_gpus, xs_gpu_c
     ctx->max_pass = std::max(1024, env_int("XSB200_MAX_PASS", 1 << 26));
     ctx->e2e_chunks = std::min<int>(kMaxChunks, std::max(0, env_int("XSB200_E2E_CHUNKS", 0)));
     {
-        // host threads that narrow the materials of a host-sample call: a share of the cores per visible GPU
-        // (one process per GPU: the ranks of a node share the host), between 2 and 8.  With fewer than 4 cores'
-        // worth per GPU the narrowing is slower than the copy it shortens (8 ranks on a 32-core host, 2 threads
-        // each: 13.0 ms per call instead of 10.7) -- the materials then travel as the caller's ints.
-        int visible = 1;
-        if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) visible = 1;
+        // host threads that narrow the materials of a host-sample call: this process's share of the cores, between
+        // 2 and 8.  The processes sharing the host are counted from the launcher's environment (torchrun / Open MPI /
+        // MPICH / Slurm; one process otherwise) times the GPUs of this context.  With fewer than 8 cores' worth per
+        // GPU the narrowing is slower than the copy it shortens -- measured on a 32-core host: 4 ranks 7.8 ms per call
+        // with, 5.6 without; 8 ranks 13.0 / 10.7 -- and the materials travel as the caller's ints.
+        int ranks = 1;
+        for (const char *name : { "LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "SLURM_NTASKS_PER_NODE" }) {
+            const int v = env_int(name, 0);
+            if (v > 0) { ranks = v; break; }
+        }
         const int cores = (int)std::thread::hardware_concurrency();
-        const int share = cores / (2 * visible);
+        const int share = cores / (2 * ranks * std::max(1, n_gpus));
         const int dflt = std::min(8, std::max(2, share));
         ctx->pack_threads = std::min(64, std::max(1, env_int("XSB200_PACK_THREADS", dflt)));
-        ctx->host_pack = env_int("XSB200_HOST_PACK", share >= 4 ? 1 : 0);
+        ctx->host_pack = env_int("XSB200_HOST_PACK", share >= 8 ? 1 : 0);
     }
     ctx->window = std::max(1, env_int("XSB200_WINDOW", 32));
     ctx->sorted_kernel = env_int("XSB200_SORTED_KERNEL", 1);
