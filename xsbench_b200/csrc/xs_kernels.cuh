@@ -1215,6 +1215,9 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
     __shared__ unsigned int s_digits[kMaxSortPasses][kRadix];   // the sort's digit counts, taken while the key is in a register
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
     if (digits.digit_hist) digit_count_zero(s_digits);
+    // the sort's top digit is (material << 4 | 4 energy bits): its counts add up to the material histogram
+    // (one shared-memory atomic per lookup less -- the one with 12 hot addresses)
+    const bool hist_from_digits = digit_top_is_material(digits);
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1242,11 +1245,12 @@ xs_sample_kernel(const Problem P, int grid_type, long first_id, long count, doub
             if (key) key[t] = k32;
             if (digits.digit_hist) digit_count_key(s_digits, digits, k32);
             if (bin_count) atomicAdd(bin_count + (k32 >> bin_shift), 1u);
-            if (mat_histogram && mine) atomicAdd(&s_hist[m], 1u);
+            if (mat_histogram && mine && !hist_from_digits) atomicAdd(&s_hist[m], 1u);
             s = apply(hop, s);
         }
     }
     __syncthreads();
+    if (hist_from_digits && threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = digit_material_count(s_digits, digits, threadIdx.x);
     if (mat_histogram && threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
         atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
     if (digits.digit_hist) digit_count_flush(s_digits, digits);
@@ -1317,6 +1321,7 @@ xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int
     __shared__ unsigned int s_digits[kMaxSortPasses][kRadix];
     if (threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = 0;
     if (digits.digit_hist) digit_count_zero(s_digits);
+    const bool hist_from_digits = key && digit_top_is_material(digits);      // (see xs_sample_kernel)
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
@@ -1339,9 +1344,10 @@ xs_locate_kernel(const Problem P, int grid_type, long count, double *energy, int
             key[t] = k32;
             if (digits.digit_hist) digit_count_key(s_digits, digits, k32);
         }
-        if (mine) atomicAdd(&s_hist[m], 1u);
+        if (mine && !hist_from_digits) atomicAdd(&s_hist[m], 1u);
     }
     __syncthreads();
+    if (hist_from_digits && threadIdx.x < kNumMaterials) s_hist[threadIdx.x] = digit_material_count(s_digits, digits, threadIdx.x);
     if (threadIdx.x < kNumMaterials && s_hist[threadIdx.x])
         atomicAdd(mat_histogram + threadIdx.x, s_hist[threadIdx.x]);
     if (digits.digit_hist) digit_count_flush(s_digits, digits);

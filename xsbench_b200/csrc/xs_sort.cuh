@@ -541,6 +541,18 @@ XS_DEV void digit_count_key(unsigned int (*h)[kRadix], const DigitSpec &spec, ui
         atomicAdd(&h[p][(k >> (spec.lo_bit + 8 * p)) & mask], 1u);
     }
 }
+// The keys the lookup pipeline sorts are (material << 28 | energy bits): when the last pass looks at bits 24..31,
+// its counts, summed over the 16 energy prefixes of a material, are the material histogram.
+XS_DEV bool digit_top_is_material(const DigitSpec &spec)
+{
+    return spec.digit_hist != nullptr && spec.last_bits == 8 && spec.lo_bit + 8 * (spec.n_passes - 1) == 24;
+}
+XS_DEV unsigned int digit_material_count(unsigned int (*h)[kRadix], const DigitSpec &spec, int m)
+{
+    unsigned int n = 0;
+    for (int i = 0; i < 16; i++) n += h[spec.n_passes - 1][16 * m + i];
+    return n;
+}
 XS_DEV void digit_count_flush(unsigned int (*h)[kRadix], const DigitSpec &spec)
 {
     for (int i = threadIdx.x; i < spec.n_passes * kRadix; i += blockDim.x)
