@@ -301,7 +301,10 @@ sort_scatter_kernel(const KeyT *__restrict__ keys_in, const uint32_t *__restrict
 #endif
 constexpr int kSweepItems = XS_ONESWEEP_ITEMS;               // keys per thread
 constexpr int kSweepTile = kSortThreads * kSweepItems;      // 4096 keys per block
-constexpr int kLookBack = 8;                                 // predecessors' words in flight per look-back round
+#ifndef XS_ONESWEEP_LOOKBACK
+#define XS_ONESWEEP_LOOKBACK 8
+#endif
+constexpr int kLookBack = XS_ONESWEEP_LOOKBACK;                                 // predecessors' words in flight per look-back round
 constexpr int kMaxSortPasses = 4;
 
 struct OnesweepScratch {
@@ -378,6 +381,24 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    // thread d: start of digit d in the whole array = keys with a smaller digit (exclusive scan of the pass's global
+    // histogram, complete before the pass starts): the same for every tile, so once per block
+    unsigned int digit_start;
+    {
+        const unsigned int mine = digit_hist[threadIdx.x];   // kSortThreads == kRadix
+        unsigned int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int t = __shfl_up_sync(kFullMask, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        digit_start = incl - mine;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) digit_start += w < warp ? s_warp_tot[w] : 0u;
+    }
+
     for (;;) {
         __syncthreads();                                    // (the previous tile's shared state is no longer read)
         if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -439,23 +460,7 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         if (tile > 0) {
             __stcg(my_status, (1u << 30) | tot);            // AGGREGATE
         }
-        // start of digit d in the whole array = digits below it (exclusive scan of the global histogram)
-        unsigned int below = digit_hist[d];
-        {
-            unsigned int incl = below;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned int t = __shfl_up_sync(kFullMask, incl, off);
-                if (lane >= off) incl += t;
-            }
-            if (lane == 31) s_warp_tot[warp] = incl;
-            __syncthreads();
-            unsigned int start = incl - below;
-#pragma unroll
-            for (int w = 0; w < kSortWarps; w++) start += w < warp ? s_warp_tot[w] : 0u;
-            below = start;
-            __syncthreads();
-        }
+        const unsigned int below = digit_start;
         unsigned int exclusive = 0;                          // keys of digit d in the tiles before this one
         int t = tile - 1;
         while (t >= 0) {
